@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: GP posterior + EI evaluations / s (FP64, batched) on N B200s - BASELINE.json metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4]
+  (N > 1: launched by torchrun, one rank per GPU)
+
+A step = one pass of the hot path over one batch: for every (GP, candidate) pair the fused kernel K4 produces the
+posterior mean, variance and the EI score plus the per-GP arg-min (and, for N > 1, the NCCL all-gather of the
+per-GP (score, index) records).  Workload = BASELINE.json configs[2] ("synthetic batched GP inference: 65,536
+independent GPs, n=64, d=3, 4,096 EI candidates each"), per GPU (weak scaling: GPs are independent units).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'GP posterior+EI evals/sec (FP64, batched)'
+UNIT = 'evals/s'
+
+
+def flops_eval(n, d):
+    """Algorithmic flops per (GP, candidate) evaluation (SURVEY.md par. 8d): dense quadratic form as the reference
+    writes it (utilities_2.py:267-268) + cross-covariance + mean + epilogue; transcendentals not counted."""
+    return 2 * n * n + n * (3 * d + 6) + 2 * d + 30
+
+
+def flops_nlml(n, d):
+    return n ** 3 / 3 + 2 * n * n + (n * n / 2) * (3 * d + 2) + 4 * n
+
+
+def fp64_peak():
+    """FP64 roofline denominator: MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 figure is the one
+    measured on this pool's B200 by tools/fp64_peaks.cu (DMMA.8x8x4 and DFMA share one pipe: 37.1 / 36.7 TFLOP/s)."""
+    path = os.path.join(REPO, 'profiles', 'r01_fp64_peaks.json')
+    try:
+        with open(path) as fh:
+            j = json.load(fh)
+        return max(j['dmma884_tflops_sustained'], j['dfma_tflops_sustained']), 'measured (tools/fp64_peaks.cu -> profiles/r01_fp64_peaks.json)'
+    except Exception:
+        return 37.2, 'nominal (148 SM x 64 FP64 FMA/clk x 1.965 GHz)'
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as fh:
+            return json.load(fh)['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def _cpu_worker(args):
+    """Faithful restatement of the reference's per-candidate call structure (oracle, kind='port'), one BLAS thread."""
+    seed, n_gp, n, d, m = args
+    from threadpoolctl import threadpool_limits
+    from gp_rto_ei_b200 import workloads
+    from oracle import gp_oracle as O
+    with threadpool_limits(1):
+        w = workloads.cfg3_numpy(seed=seed, B=n_gp, n=n, d=d, m=m)
+        gps = [O.make_gp(w['X'][b], w['y'][b], w['theta'][b]) for b in range(n_gp)]
+        t0 = time.perf_counter()
+        acc = 0.0
+        for b in range(n_gp):
+            _, _, s = O.posterior_acq_scalar(w['cand'][b], gps[b], None, w['f_best'][b], 3)
+            acc += float(s.min())
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        for b in range(n_gp):
+            O.posterior_acq_vectorised(w['cand'][b], gps[b], None, w['f_best'][b], 3)
+        dtv = time.perf_counter() - t1
+    return dt, dtv, acc
+
+
+def cpu_baseline_run(n, d, gps_per_core=1, m=2048, cores=None):
+    """Bounded sample of the same workload on all host cores: `cores` processes x gps_per_core GPs x m candidates."""
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
+    ctx = mp.get_context('spawn')
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, gps_per_core, n, d, m) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    evals = cores * gps_per_core * m
+    t_scalar = max(r[0] for r in res)
+    t_vec = max(r[1] for r in res)
+    return {'value': evals / t_scalar, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d processes x %d GP x %d candidates (n=%d, d=%d), oracle/gp_oracle.posterior_acq_scalar = the reference\'s '
+                      'one-candidate-at-a-time GP_obj_f -> GP_inference_np call structure, 1 BLAS thread per process' % (cores, gps_per_core, m, n, d),
+            'per_core': evals / t_scalar / cores, 'vectorised_numpy_value': evals / t_vec, 'pool_wall_s': wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    n, d, m = 64, 3, 4096
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline_run(n, d, gps_per_core=1, m=512)
+        if i >= args.warmup:
+            vals.append(r)
+    v = sum(x['value'] for x in vals) / len(vals)
+    evals_per_step = vals[0]['cores'] * 512
+    line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * evals_per_step / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': {'workload': 'cfg3: synthetic batched GP inference, 65,536 GPs x 4,096 EI candidates, n=64, d=3 '
+                                            '(bounded sample per step, see cpu_baseline.sample)'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': vals[0]['cores'], 'kind': 'port', 'sample': vals[0]['sample'],
+                             'vectorised_numpy_value': sum(x['vectorised_numpy_value'] for x in vals) / len(vals)},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gp_rto_ei_b200 import api, parallel, workloads
+
+    rank, local_rank, world = parallel.init()
+    if world != args.gpus:
+        if rank == 0:
+            print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    h = api.Handle(local_rank)
+
+    n, d = args.n, args.d
+    B, m = args.B, args.m
+    w = workloads.cfg3_torch(dev, seed=1000 * rank, B=B, n=n, d=d, m=m)
+    gd = h.fit_fixed(w['X'], w['y'], w['theta'])            # K2 (outside the timed region: the metric is K4)
+    assert int(gd['status'].abs().sum()) == 0
+    cand, f_best = w['cand'], w['f_best']
+    mean = torch.empty(B, m, dtype=torch.float64, device=dev)
+    var = torch.empty_like(mean); score = torch.empty_like(mean)
+    best_s = torch.empty(B, dtype=torch.float64, device=dev); best_i = torch.empty(B, dtype=torch.int64, device=dev)
+    rec = torch.empty(B, 2, dtype=torch.float64, device=dev)
+    lib, hp, P = h.lib, h._h, api._ptr
+    lo, _ = parallel.shard_range(B * world, rank, world)
+
+    def step():
+        api._lib.check(lib.gprto_posterior_acq(hp, B, n, d, m, P(gd['Xn']), P(gd['invK']), P(gd['alpha']), P(gd['theta']), P(gd['x_mean']),
+                                               P(gd['x_std']), P(gd['y_mean']), P(gd['y_std']), P(cand), None, P(f_best), 3, P(mean), P(var),
+                                               P(score), P(best_s), P(best_i), h._stream()), 'gprto_posterior_acq')
+        if world > 1:
+            api._lib.check(lib.gprto_pack_best(hp, B, P(best_s), P(best_i), 0, P(rec), h._stream()), 'gprto_pack_best')
+            return parallel.allgather_records(rec)
+        return None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = h.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        evk[i][0].record()
+        step()
+        evk[i][1].record()
+    e1.record()
+    sync_all()
+    launches = h.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t[0])
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    evals_step = float(B) * m * world
+    value = evals_step / (ms_step * 1e-3)
+    k4_ms = sum(a.elapsed_time(b) for a, b in evk) / args.steps      # per-step device time on this rank (K4 dominates)
+
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'ms_per_step': ms_step, 'kernel_ms': k4_ms, 'gpu_launches': launches}))
+        return
+
+    # ---- e2e: host buffers through the C-ABI host entry (H2D of candidates, D2H of mean/var/score/best inside the timed region)
+    Be = min(B, args.e2e_B)
+    cand_h = torch.empty(Be, m, d, dtype=torch.float64).pin_memory()
+    cand_h.copy_(cand[:Be])
+    outs = dict(mean=torch.empty(Be, m, dtype=torch.float64).pin_memory(), var=torch.empty(Be, m, dtype=torch.float64).pin_memory(),
+                score=torch.empty(Be, m, dtype=torch.float64).pin_memory(), best_score=torch.empty(Be, dtype=torch.float64).pin_memory(),
+                best_idx=torch.empty(Be, dtype=torch.int64).pin_memory())
+    gsub = {k: v[:Be] for k, v in gd.items()}
+    fb = f_best[:Be]
+    for _ in range(2):
+        h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs)       # returns after the last D2H completed
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = float(Be) * m * world * e2e_steps / float(t[0])
+    assert torch.equal(outs['score'][:4], score[:4].cpu())
+    h2d = Be * m * d * 8
+    d2h = Be * m * 3 * 8 + Be * 16
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---- parity sample against the oracle (outside the timed region)
+    from oracle import gp_oracle as O
+    npar = 8
+    worst = {'mean': 0.0, 'var': 0.0, 'score': 0.0, 'argmin_mismatch': 0}
+    Xh, yh, th = w['X'][:npar].cpu().numpy(), w['y'][:npar].cpu().numpy(), w['theta'][:npar].cpu().numpy()
+    ch, fh = cand[:npar].cpu().numpy(), f_best[:npar].cpu().numpy()
+    for b in range(npar):
+        gp = O.make_gp(Xh[b], yh[b], th[b])
+        mv, vv, sv = O.posterior_acq_vectorised(ch[b], gp, None, fh[b], 3)
+        sf2 = math.exp(2 * th[b][d])
+        worst['mean'] = max(worst['mean'], float(np.max(np.abs(mean[b].cpu().numpy() - mv) / np.abs(mv))))
+        worst['var'] = max(worst['var'], float(np.max(np.abs(var[b].cpu().numpy() - vv) / np.maximum(np.abs(vv), 1e-6 * sf2 * gp['Y_std'] ** 2))))
+        worst['score'] = max(worst['score'], float(np.max(np.abs(score[b].cpu().numpy() - sv)) / np.max(np.abs(sv))))
+        worst['argmin_mismatch'] += int(int(best_i[b]) != int(np.argmin(sv)))
+
+    cpu = cpu_baseline_run(n, d, gps_per_core=1, m=2048)
+    peak, peak_src = fp64_peak()
+    F = flops_eval(n, d)
+    achieved = (float(B) * m * F) / (k4_ms * 1e-3) / 1e12
+    hbm, hbm_src = hbm_peak()
+    alg_bytes = 8.0 * (d + 3) + 8.0 * (n * n + n * d + n + 3 * d + 4) / m
+    traffic = None
+    try:
+        with open(os.path.join(REPO, 'profiles', 'k4_ncu_summary.json')) as fh_:
+            traffic = json.load(fh_).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'cfg3 (BASELINE.json configs[2]): synthetic batched GP inference, %d independent GPs per GPU, n=%d, d=%d, '
+                               '%d EI candidates each; outputs mean+var+score per candidate and per-GP arg-min' % (B, n, d, m),
+                   'gps_per_gpu': B, 'n': n, 'd': d, 'candidates_per_gp': m, 'acq': 'EI', 'parallelism': 'gp-sharded x%d' % world,
+                   'l2': 'inputs per step (%.1f GB candidates + %.1f GB invK) exceed the 126 MB L2; no flush needed' %
+                         (B * m * d * 8 / 1e9, B * n * n * 8 / 1e9),
+                   'collective': 'NCCL all-gather of per-GP (score, idx) records each step' if world > 1 else 'none (single GPU)'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'sample': 'gprto_posterior_acq_host on %d GPs x %d candidates per GPU, pinned host buffers, %d steps' % (Be, m, e2e_steps)},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'kernel': 'k4_dmma_kernel<8,3>', 'kernel_ms': k4_ms, 'flops_per_eval': F, 'peak_source': 'FP64 ' + peak_src +
+                     '; FP64 DMMA and DFMA share one pipe on B200, MEASURED_PEAKS.json has no FP64 entry',
+                     'hbm_check': {'algorithmic_bytes_per_eval': alg_bytes, 'achieved_gbs': float(B) * m * alg_bytes / (k4_ms * 1e-3) / 1e9,
+                                   'peak_gbs': hbm, 'peak_source': hbm_src}},
+        'cpu_baseline': cpu,
+        'parity': {'sample': '%d GPs x %d candidates vs oracle (vectorised NumPy restatement)' % (npar, m), 'max_rel_err': worst},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--B', type=int, default=65536)
+    ap.add_argument('--m', type=int, default=4096)
+    ap.add_argument('--n', type=int, default=64)
+    ap.add_argument('--d', type=int, default=3)
+    ap.add_argument('--e2e-B', dest='e2e_B', type=int, default=16384)
+    ap.add_argument('--skip-extras', action='store_true', help='profiling runs: no e2e / CPU baseline / parity legs')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == '__main__':
+    main()

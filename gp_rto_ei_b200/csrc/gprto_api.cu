@@ -304,7 +304,7 @@ int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* X
   if (!h || B <= 0 || S <= 0 || n <= 0 || d <= 0 || !Xn || !theta || !K) return GPRTO_EINVAL;
   if (d > CH_MAXD || size_t(n) * d * sizeof(double) > 200 * 1024) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
-  const size_t smem = size_t(n) * d * sizeof(double);
+  const size_t smem = (size_t(n) * d + CH_MAXD) * sizeof(double);
   int rc = set_smem(cov_kernel, smem);
   if (rc) return rc;
   cov_kernel<<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, K);

@@ -15,18 +15,18 @@ inline size_t ch_smem_bytes(int n, int d) {
   return sizeof(double) * (size_t(n) * ch_ld(n) + size_t(n) * d + 2 * size_t(n) + 2 * CH_MAXD + 8);
 }
 
-// Scaled inputs: Xs[j][dd] = Xn[j][dd] * exp(-theta_dd) * sqrt(.5), so that
-// K_ij = exp(2 theta_sf - sum_dd (Xs_i - Xs_j)^2) = sf2 * exp(-.5 * sum (x_i-x_j)^2 / W).
+// K_ij = exp(2 theta_sf + sum_dd (x_i - x_j)^2 * nhw_dd),  nhw_dd = -1/(2 W_dd) = -0.5 exp(-2 theta_dd).
+// The difference is formed BEFORE scaling so its rounding error stays relative to |x_i - x_j| (as in the
+// reference's cdist); scaling the points first loses ~length-scale^-1 digits on near-duplicate points, which
+// cond(K) then amplifies in the NLML.
 __device__ __forceinline__ void ch_stage_inputs(const double* __restrict__ Xn, const double* __restrict__ theta,
-                                                int n, int d, double* Xs) {
-  for (int e = threadIdx.x; e < n * d; e += blockDim.x) {
-    const int dd = e % d;
-    Xs[e] = Xn[e] * exp(-theta[dd]) * 0.70710678118654752440;
-  }
+                                                int n, int d, double* Xs, double* nhw) {
+  for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xs[e] = Xn[e];
+  if (threadIdx.x < d) nhw[threadIdx.x] = -0.5 * exp(-2.0 * theta[threadIdx.x]);
 }
 
-__device__ __forceinline__ void ch_build_K(const double* Xs, int n, int d, double c0, double diag_add, double* A,
-                                           int ld) {
+__device__ __forceinline__ void ch_build_K(const double* Xs, const double* nhw, int n, int d, double c0,
+                                           double diag_add, double* A, int ld) {
   // lower triangle incl. diagonal, mirrored into the upper triangle
   const int total = n * (n + 1) / 2;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
@@ -37,7 +37,7 @@ __device__ __forceinline__ void ch_build_K(const double* Xs, int n, int d, doubl
     double acc = c0;
     for (int dd = 0; dd < d; ++dd) {
       const double df = Xs[i * d + dd] - Xs[j * d + dd];
-      acc = fma(-df, df, acc);
+      acc = fma(df * df, nhw[dd], acc);
     }
     double v = exp_fast(acc);
     if (i == j) v += diag_add;
@@ -89,16 +89,17 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   double* A = reinterpret_cast<double*>(smem_raw);
   double* Xs = A + size_t(n) * ld;
   double* z = Xs + n * d;
+  double* nhw = z + 2 * n;
   __shared__ int s_info;
   __shared__ double s_logdet;
   const int64_t bs = blockIdx.x;
   const int64_t b = bs / S;
   const double* theta = theta_all + bs * (d + 2);
-  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs);
+  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = Yn[b * n + i];
   __syncthreads();
   const double sn2 = exp(2.0 * theta[d + 1]);
-  ch_build_K(Xs, n, d, 2.0 * theta[d], sn2 + jitter, A, ld);
+  ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], sn2 + jitter, A, ld);
   __syncthreads();
   ch_cholesky(A, n, ld, &s_info, &s_logdet);
   __syncthreads();
@@ -130,10 +131,11 @@ __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, co
                                                          double jitter, double* __restrict__ K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Xs = reinterpret_cast<double*>(smem_raw);
+  double* nhw = Xs + n * d;
   const int64_t bs = blockIdx.x;
   const int64_t b = bs / S;
   const double* theta = theta_all + bs * (d + 2);
-  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs);
+  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   __syncthreads();
   const double diag = (add_noise ? exp(2.0 * theta[d + 1]) : 0.0) + jitter;
   const double c0 = 2.0 * theta[d];
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, co
     double acc = c0;
     for (int dd = 0; dd < d; ++dd) {
       const double df = Xs[hi * d + dd] - Xs[lo * d + dd];
-      acc = fma(-df, df, acc);
+      acc = fma(df * df, nhw[dd], acc);
     }
     double v = exp_fast(acc);
     if (i == j) v += diag;
@@ -165,14 +167,15 @@ __global__ void __launch_bounds__(CH_THREADS) factor_generic_kernel(int n, int d
   double* Xs = A + size_t(n) * ld;
   double* y = Xs + n * d;
   double* z = y + n;
+  double* nhw = z + n;
   __shared__ int s_info;
   __shared__ double s_logdet;
   const int64_t b = blockIdx.x;
   const double* theta = theta_all + b * (d + 2);
-  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs);
+  ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = Yn[b * n + i];
   __syncthreads();
-  ch_build_K(Xs, n, d, 2.0 * theta[d], exp(2.0 * theta[d + 1]) + jitter, A, ld);
+  ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], exp(2.0 * theta[d + 1]) + jitter, A, ld);
   __syncthreads();
   ch_cholesky(A, n, ld, &s_info, &s_logdet);
   __syncthreads();

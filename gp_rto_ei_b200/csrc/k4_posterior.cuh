@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
   constexpr int NS = 2 * NB;       // k-steps
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Mf = reinterpret_cast<double*>(smem_raw);          // [frags][32]
-  double* Xs = Mf + k4_frags<NB>() * 32;                     // [NP][D] scaled data points
+  double* Xs = Mf + k4_frags<NB>() * 32;                     // [NP][D] normalised data points
   double* As = Xs + NP * D;                                  // [NP] alpha
   double* cs = As + NP;                                      // [D] candidate scale a_d
   double* cm = cs + D;                                       // [D] x_mean
-  double* sc = cm + D;                                       // [D] (unused pad) then scalars
+  double* sc = cm + D;                                       // [D] -1/(2 W_d)
   double* scal = sc + D;                                     // [8]: c0, sf2, y_std, y_mean, f_best
   double* red_s = scal + 8;                                  // [warps]
   int64_t* red_i = reinterpret_cast<int64_t*>(red_s + K4_WARPS);
@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
   }
   for (int e = tid; e < NP * D; e += K4_THREADS) {
     const int j = e / D, dd = e - j * D;
-    // (x - X)^2 / W * 0.5  ==  ((x - X) * exp(-theta) * sqrt(.5))^2
-    Xs[e] = j < n ? p.Xn[(b * n + j) * D + dd] * exp(-theta[dd]) * 0.70710678118654752440 : 0.0;
+    Xs[e] = j < n ? p.Xn[(b * n + j) * D + dd] : 0.0;
   }
   for (int e = tid; e < NP; e += K4_THREADS) As[e] = e < n ? p.alpha[b * n + e] : 0.0;
   if (tid < D) {
-    cs[tid] = exp(-theta[tid]) * 0.70710678118654752440 / p.x_std[b * D + tid];
+    cs[tid] = 1.0 / p.x_std[b * D + tid];
     cm[tid] = p.x_mean[b * D + tid];
+    sc[tid] = -0.5 * exp(-2.0 * theta[tid]);      // -1/(2 W_d)
   }
   if (tid == 0) {
     scal[0] = 2.0 * theta[D];
@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
   __syncthreads();
 
   const double c0 = scal[0], sf2 = scal[1], y_std = scal[2], y_mean = scal[3], f_best = scal[4];
-  double a_d[D], mu_d[D];
+  double a_d[D], mu_d[D], nhw[D];
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) { a_d[dd] = cs[dd]; mu_d[dd] = cm[dd]; }
+  for (int dd = 0; dd < D; ++dd) { a_d[dd] = cs[dd]; mu_d[dd] = cm[dd]; nhw[dd] = sc[dd]; }
 
   const int64_t c_begin = int64_t(blockIdx.x) * p.chunk;
   const int64_t c_end = min(p.m, c_begin + p.chunk);
@@ -131,8 +131,10 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
         double acc = c0;
 #pragma unroll
         for (int dd = 0; dd < D; ++dd) {
+          // difference first, scale second: keeps the rounding error relative to |x - X| (as the reference's
+          // cdist does) instead of to |x|/length-scale
           const double df = x[dd] - Xt[(8 * (s >> 1) + (s & 1)) * D + dd];
-          acc = fma(-df, df, acc);
+          acc = fma(df * df, nhw[dd], acc);
         }
         kv[s] = exp_fast(acc);
       }
