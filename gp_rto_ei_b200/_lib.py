@@ -4,7 +4,7 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgprto.so')
+LIB_PATH = os.environ.get('GPRTO_LIB', os.path.join(HERE, 'libgprto.so'))   # GPRTO_LIB: A/B builds of the same ABI
 
 EINVAL, EUNSUPPORTED, ENODEVICE, ENOMEM = -10001, -10002, -10003, -10004
 ACQ_MEAN, ACQ_LCB, ACQ_EI = 1, 2, 3

@@ -84,7 +84,7 @@ int launch_k4_dmma(gprto_t* h, const K4Params& p, cudaStream_t s) {
     if (rc) return rc;
     configured = true;
   }
-  dim3 grid(p.nchunks, (unsigned)p.B);
+  dim3 grid((unsigned)p.B, p.nchunks);      // GP on x (2^31-1 limit), candidate chunk on y
   k4_dmma_kernel<NB, D><<<grid, K4_THREADS, smem, s>>>(p);
   h->launches++;
   return launch_status();
@@ -134,19 +134,6 @@ int posterior_device(gprto_t* h, int64_t B, int n, int d, int64_t m, const doubl
   if (h->k4_path == GPRTO_K4_GENERIC) use_dmma = false;
   if (h->k4_path == GPRTO_K4_DMMA && !dmma_ok) return GPRTO_EUNSUPPORTED;
   if (!use_dmma && (n > K4G_MAXN || d > K4G_MAXD)) return GPRTO_EUNSUPPORTED;
-  if (B > 65535) {   // gridDim.y limit: split the GP range
-    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
-      const int64_t bn = std::min<int64_t>(65535, B - b0);
-      int rc = posterior_device(h, bn, n, d, m, Xn + b0 * n * d, invK + b0 * int64_t(n) * n, alpha + b0 * n,
-                                theta_opt + b0 * (d + 2), x_mean + b0 * d, x_std + b0 * d, y_mean + b0, y_std + b0,
-                                cand + b0 * m * d, prior ? prior + b0 * m : nullptr, f_best ? f_best + b0 : nullptr, acq,
-                                mean ? mean + b0 * m : nullptr, var ? var + b0 * m : nullptr,
-                                score ? score + b0 * m : nullptr, best_score ? best_score + b0 : nullptr,
-                                best_idx ? best_idx + b0 : nullptr, s);
-      if (rc) return rc;
-    }
-    return 0;
-  }
   K4Params p{};
   p.B = B; p.m = m; p.n = n; p.d = d; p.acq = acq;
   p.Xn = Xn; p.invK = invK; p.alpha = alpha; p.theta = theta_opt; p.x_mean = x_mean; p.x_std = x_std;
@@ -160,6 +147,7 @@ int posterior_device(gprto_t* h, int64_t B, int n, int d, int64_t m, const doubl
   int64_t chunk = ((m + nchunks - 1) / nchunks + gran - 1) / gran * gran;
   chunk = std::max<int64_t>(chunk, gran);
   nchunks = (m + chunk - 1) / chunk;
+  if (nchunks > 65535) return GPRTO_EUNSUPPORTED;
   p.chunk = chunk;
   p.nchunks = int(nchunks);
   if (best_score) {
@@ -173,7 +161,7 @@ int posterior_device(gprto_t* h, int64_t B, int n, int d, int64_t m, const doubl
   int rc;
   if (use_dmma) rc = dispatch_k4(h, p, s);
   else {
-    dim3 grid(p.nchunks, (unsigned)B);
+    dim3 grid((unsigned)B, p.nchunks);
     k4_generic_kernel<<<grid, K4G_THREADS, 0, s>>>(p);
     h->launches++;
     rc = launch_status();

@@ -19,6 +19,9 @@ struct K4Params {
 
 constexpr int K4_WARPS = 4;
 constexpr int K4_THREADS = K4_WARPS * 32;
+#ifndef K4_MINB
+#define K4_MINB 4
+#endif
 
 // Data index handled by k-step s on a lane with threadID-in-group t: within an 8-block the four
 // lanes of a quad own {2t, 2t+1}, which is exactly the pair of output columns the same lane holds in
@@ -42,7 +45,7 @@ __host__ __device__ constexpr size_t k4_smem_bytes() {
 //   C accumulators                              = (M k*) for the lane's own data points
 // Only the NB(NB+1) non-zero fragments of the triangular M are visited: n(n+1)/2-type work instead of n^2.
 template <int NB, int D>
-__global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
+__global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_kernel(const K4Params p) {
   constexpr int NP = 8 * NB;       // padded n
   constexpr int NS = 2 * NB;       // k-steps
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t b = blockIdx.y;
+  const int64_t b = blockIdx.x;
   const int n = p.n;
   const double* theta = p.theta + b * (D + 2);
   const double* invK = p.invK + b * int64_t(n) * n;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
 #pragma unroll
   for (int dd = 0; dd < D; ++dd) { a_d[dd] = cs[dd]; mu_d[dd] = cm[dd]; nhw[dd] = sc[dd]; }
 
-  const int64_t c_begin = int64_t(blockIdx.x) * p.chunk;
+  const int64_t c_begin = int64_t(blockIdx.y) * p.chunk;
   const int64_t c_end = min(p.m, c_begin + p.chunk);
   const double* cand = p.cand + b * p.m * D;
   const double* Xt = Xs + 2 * t * D;       // + (8*(s>>1) + (s&1))*D + dd   (compile-time offsets)
@@ -190,8 +193,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_dmma_kernel(const K4Params p) {
     if (tid == 0) {
       for (int w = 1; w < K4_WARPS; ++w)
         if (better(red_s[w], red_i[w], best_v, best_i)) { best_v = red_s[w]; best_i = red_i[w]; }
-      p.part_score[b * p.nchunks + blockIdx.x] = best_v;
-      p.part_idx[b * p.nchunks + blockIdx.x] = best_i;
+      p.part_score[b * p.nchunks + blockIdx.y] = best_v;
+      p.part_idx[b * p.nchunks + blockIdx.y] = best_i;
     }
   }
 }
@@ -204,7 +207,7 @@ constexpr int K4G_MAXD = 16;
 constexpr int K4G_THREADS = 128;
 
 __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params p) {
-  const int64_t b = blockIdx.y;
+  const int64_t b = blockIdx.x;
   const int n = p.n, d = p.d;
   const double* theta = p.theta + b * (d + 2);
   const double* invK = p.invK + b * int64_t(n) * n;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
   const double sf2 = exp(2.0 * theta[d]);
   const double y_std = p.y_std[b], y_mean = p.y_mean[b];
   const double f_best = p.f_best ? p.f_best[b] : 0.0;
-  const int64_t c_begin = int64_t(blockIdx.x) * p.chunk;
+  const int64_t c_begin = int64_t(blockIdx.y) * p.chunk;
   const int64_t c_end = min(p.m, c_begin + p.chunk);
   double best_v = CUDART_INF;
   int64_t best_i = INT64_MAX;
@@ -267,8 +270,8 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
     if (threadIdx.x == 0) {
       for (int w = 1; w < K4G_THREADS / 32; ++w)
         if (better(red_s[w], red_i[w], best_v, best_i)) { best_v = red_s[w]; best_i = red_i[w]; }
-      p.part_score[b * p.nchunks + blockIdx.x] = best_v;
-      p.part_idx[b * p.nchunks + blockIdx.x] = best_i;
+      p.part_score[b * p.nchunks + blockIdx.y] = best_v;
+      p.part_idx[b * p.nchunks + blockIdx.y] = best_i;
     }
   }
 }

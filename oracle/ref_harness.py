@@ -6,6 +6,7 @@ skipped when the reference is absent.  The three modules the reference imports b
 lacks (casadi, matplotlib, sobol_seq) are provided from oracle/stubs.
 """
 import importlib
+import importlib.util
 import os
 import sys
 
@@ -18,26 +19,26 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, 'sub_uts', 'utilities_2.py'))
 
 
-def load():
-    """Return the reference's sub_uts.utilities_2 module object (imported as `_ref_utilities_2`)."""
+def load(name='utilities_2'):
+    """Return the reference's sub_uts.<name> module object (imported as `_ref_<name>`); name = utilities_2 | systems."""
     if not available():
         raise RuntimeError('reference tree not present at %s' % REFERENCE_ROOT)
-    if '_ref_utilities_2' in sys.modules:
-        return sys.modules['_ref_utilities_2']
+    modname = '_ref_' + name
+    if modname in sys.modules:
+        return sys.modules[modname]
     saved = list(sys.path)
     try:
-        for name in ('casadi', 'matplotlib', 'sobol_seq'):
+        for dep in ('casadi', 'matplotlib', 'sobol_seq'):
             try:
-                importlib.import_module(name)
+                importlib.import_module(dep)
             except ImportError:
                 if _STUBS not in sys.path:
                     sys.path.insert(0, _STUBS)
         if _REPO not in sys.path:
             sys.path.insert(0, _REPO)
-        spec = importlib.util.spec_from_file_location(
-            '_ref_utilities_2', os.path.join(REFERENCE_ROOT, 'sub_uts', 'utilities_2.py'))
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(REFERENCE_ROOT, 'sub_uts', name + '.py'))
         mod = importlib.util.module_from_spec(spec)
-        sys.modules['_ref_utilities_2'] = mod
+        sys.modules[modname] = mod
         spec.loader.exec_module(mod)
         return mod
     finally:

@@ -13,6 +13,8 @@ Files written
   cfg3_small.npz    4 synthetic cfg-3 GPs (n=64, d=3, 256 candidates): Cov_mat, invK, mean/var, EI/LCB/mean.
   cfg4_small.npz    2 synthetic cfg-4 GPs (n=128, d=3) x 64 Sobol starts: negative_loglikelihood
                     (nan + flag where the reference raises LinAlgError).
+  rto_simple.npz    three short seeded episodes of the reference's ITR_GP_RTO on the toy problem (trajectories, TR radii,
+                    backtrack flags).
   ragged.npz        edge cases: n=1, n=2, n=7 (not a multiple of 8), d=1 and d=5, zero variance (candidate on a
                     noise-free data point), far-tail EI.
 """
@@ -183,9 +185,79 @@ def ragged():
     np.savez_compressed(os.path.join(HERE, 'ragged.npz'), **out)
 
 
+def rto_simple():
+    """Short seeded episodes of the reference's own ITR_GP_RTO on the toy problem (arguments of
+    run_simple/main_simple.py:179-206 with fewer iterations/starts): noiseless plant (deterministic given the seeds)
+    and the noisy plant of the script (checks the RNG consumption order)."""
+    import contextlib
+    import io
+    import random
+    rsys = ref_harness.load('systems')
+    out = {}
+    for tag, plant, cons, acq, noise in (('noiseless_ei', rsys.Benoit_System_noiseless, rsys.con1_system_tight_noiseless, 3, None),
+                                         ('noisy_ei', rsys.Benoit_System, rsys.con1_system_tight, 3, [1e-3] * 2),
+                                         ('noiseless_lcb', rsys.Benoit_System_noiseless, rsys.con1_system_tight_noiseless, 2, None)):
+        def episode():
+            np.random.seed(0); random.seed(0)
+            Xtrain = np.array([[1.2, 0.], [1.4, 0.1], [1.3, -0.1]])
+            with contextlib.redirect_stdout(io.StringIO()):
+                rto = ref.ITR_GP_RTO(rsys.Benoit_Model, plant, [rsys.con1_model], [cons], np.array([1.1, -0.1]), 0.25, 0.7, 0.2, 0.8,
+                                     0.8, 1.2, 4, ['data0', Xtrain], np.array([[-.6, 1.5], [-1., 1.]]), obj_setting=acq, noise=noise,
+                                     multi_opt=6, multi_hyper=4, TR_scaling=False, TR_curvature=False, store_data=True, inner_TR=False,
+                                     scale_inputs=False)
+                return rto.RTO_routine()
+        X_opt, y_opt, TR_l, xnew, backtrack = episode()
+        # Chaotic case (LCB, free noise, 4 data points): an ensemble of the reference under RELATIVE perturbations of its
+        # NLML of 1e-15 ... 1e-12 - the trust-region sequence itself flips between two branches.
+        if tag == 'noiseless_lcb':
+            nll_nom = ref.GP_model.negative_loglikelihood
+            ens_X, ens_TR = [], []
+            for e, rel in enumerate((1e-15, 1e-14, 1e-13, 3e-13, 1e-12, 1e-11)):
+                rng = np.random.default_rng(99 + e)
+
+                def nll_p(self, hyper, X, Y, rel=rel, rng=rng):
+                    return nll_nom(self, hyper, X, Y) * (1 + rel * rng.standard_normal())
+                ref.GP_model.negative_loglikelihood = nll_p
+                try:
+                    o = episode()
+                finally:
+                    ref.GP_model.negative_loglikelihood = nll_nom
+                ens_X.append(o[0]); ens_TR.append(np.array(o[2], dtype=float))
+                print('   ensemble rel=%g TR %s max|dX| %.2e' % (rel, o[2], np.abs(o[0] - X_opt).max()))
+            out[tag + '_ens_X'] = np.stack(ens_X); out[tag + '_ens_TR'] = np.stack(ens_TR)
+        # Self-sensitivity of the reference: the same episode with its NLML and posterior nudged by ONE ulp
+        # (x (1 + 2^-52)).  Any other correct implementation differs from NumPy by at least that much, so the spread of
+        # the iterates under this nudge is the floor for trajectory parity (SURVEY.md par. 7.3-1).
+        nll0, inf0 = ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np
+        ulp = 1.0 + 2.0 ** -52
+
+        def nll1(self, hyper, X, Y):
+            return nll0(self, hyper, X, Y) * ulp
+
+        def inf1(self, x):
+            r = inf0(self, x)
+            return (r[0] * ulp, r[1] * ulp) if isinstance(r, tuple) else r * ulp
+        ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np = nll1, inf1
+        try:
+            Xp, yp, TRp, _, btp = episode()
+        finally:
+            ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np = nll0, inf0
+        out.update({tag + '_X_opt': X_opt, tag + '_y_opt': y_opt, tag + '_TR_l': np.array(TR_l, dtype=float),
+                    tag + '_xnew': np.asarray(xnew), tag + '_backtrack': np.array(backtrack, dtype=bool),
+                    tag + '_X_opt_ulp': Xp, tag + '_TR_l_ulp': np.array(TRp, dtype=float), tag + '_backtrack_ulp': np.array(btp, dtype=bool)})
+        print('rto', tag, 'TR', TR_l, 'backtrack', backtrack, 'x', np.asarray(xnew).ravel(),
+              '| one-ulp self-sensitivity max|dX| = %.3e, same TR/backtrack: %s' %
+              (np.abs(Xp - X_opt).max(), np.array_equal(TRp, TR_l) and list(btp) == list(backtrack)))
+    np.savez_compressed(os.path.join(HERE, 'rto_simple.npz'), **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        globals()[sys.argv[1]]()
+        sys.exit(0)
     pickle_gps()
     cfg3_small()
     cfg4_small()
     ragged()
+    rto_simple()
     print('golden vectors written to', HERE)
