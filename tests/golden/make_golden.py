@@ -212,8 +212,8 @@ def rto_simple():
         if tag == 'noiseless_lcb':
             nll_nom = ref.GP_model.negative_loglikelihood
             ens_X, ens_TR = [], []
-            for e, rel in enumerate((1e-15, 1e-14, 1e-13, 3e-13, 1e-12, 1e-11)):
-                rng = np.random.default_rng(99 + e)
+            for e, (rel, sd) in enumerate([(r, 99) for r in (1e-15, 1e-14, 1e-13, 1e-12)] + [(1e-13, q) for q in range(100, 108)]):
+                rng = np.random.default_rng(sd)
 
                 def nll_p(self, hyper, X, Y, rel=rel, rng=rng):
                     return nll_nom(self, hyper, X, Y) * (1 + rel * rng.standard_normal())
@@ -223,7 +223,7 @@ def rto_simple():
                 finally:
                     ref.GP_model.negative_loglikelihood = nll_nom
                 ens_X.append(o[0]); ens_TR.append(np.array(o[2], dtype=float))
-                print('   ensemble rel=%g TR %s max|dX| %.2e' % (rel, o[2], np.abs(o[0] - X_opt).max()))
+                print('   ensemble rel=%g seed=%d TR %s max|dX| %.2e' % (rel, sd, o[2], np.abs(o[0] - X_opt).max()))
             out[tag + '_ens_X'] = np.stack(ens_X); out[tag + '_ens_TR'] = np.stack(ens_TR)
         # Self-sensitivity of the reference: the same episode with its NLML and posterior nudged by ONE ulp
         # (x (1 + 2^-52)).  Any other correct implementation differs from NumPy by at least that much, so the spread of
