@@ -82,6 +82,7 @@ int launch_k4_dmma(gprto_t* h, const K4Params& p, cudaStream_t s) {
   if (!configured) {
     int rc = set_smem(k4_dmma_kernel<NB, D>, smem);
     if (rc) return rc;
+    cudaFuncSetAttribute(k4_dmma_kernel<NB, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   dim3 grid((unsigned)p.B, p.nchunks);      // GP on x (2^31-1 limit), candidate chunk on y

@@ -61,6 +61,21 @@ __device__ __forceinline__ double acquisition(int acq, double mean, double var, 
   return -(sigma * pdf + delta * cdf);
 }
 
+// 1/sqrt(x) for normal positive x: hardware seed (rsqrt.approx.f64, ~2^-22) + two Newton steps (6 dependent FP64
+// instructions, relative error ~1e-16).  Non-positive or NaN x yields NaN/inf, which the callers flag beforehand.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double u = h * y;
+  double t = fma(-u, y, 0.5);
+  y = fma(y, t, y);
+  u = h * y;
+  t = fma(-u, y, 0.5);
+  y = fma(y, t, y);
+  return y;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
