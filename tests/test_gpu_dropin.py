@@ -104,3 +104,28 @@ def test_rto_episode_matches_reference(u2, tag, acq, noisy):
     assert np.abs(X_opt - g[tag + '_X_opt']).max() < tol
     if not noisy:
         assert np.abs(y_opt - g[tag + '_y_opt']).max() < 10 * tol
+
+
+def test_run_main_executes_a_reference_style_driver(u2, tmp_path):
+    """gp_rto_ei_b200/run_main.py: a script with the reference's import header (casadi / matplotlib / sobol_seq /
+    plots_RTO star-imports, `from sub_uts.utilities_2 import *`) runs unchanged on this package; one full-size episode
+    (20 RTO iterations, 30 acquisition starts, 15 hyper-parameter starts - the arguments of run_simple/main_simple.py:
+    179-206) and the result pickle has the reference's structure.  The reference needs ~26 s per episode on 8 CPU
+    cores (SURVEY.md par. 6)."""
+    import os
+    import pickle
+    from conftest import REPO
+    from gp_rto_ei_b200 import run_main
+    with contextlib.redirect_stdout(io.StringIO()):
+        glob, out = run_main.run(os.path.join(REPO, 'tests', 'data', 'mini_main_simple.py'), episodes=1, out=str(tmp_path))
+    print('\n[run_main] one full episode (20 iterations): %.2f s' % glob['episode_seconds'])
+    with open(os.path.join(out, 'with_prior_with_exploration_ei_noise.p'), 'rb') as fh:
+        X_opt_mc, y_opt_mc, TR_l_mc, xnew_mc, backtrack_mc = pickle.load(fh)
+    assert len(X_opt_mc) == 1 and X_opt_mc[0].shape == (24, 2) and y_opt_mc[0].shape == (2, 24)
+    assert len(TR_l_mc[0]) == 21 and len(backtrack_mc[0]) == 21
+    # solution quality anchor (BASELINE.md par. 3): the noise-free objective of the final iterate is in the range of the
+    # reference's shipped runs for this setting (0.13 ... 1.06), and the iterate respects the input bounds
+    from gp_rto_ei_b200.sub_uts import systems as S
+    f = S.Benoit_System_noiseless(np.asarray(xnew_mc[0]).flatten())
+    assert 0.05 < f < 1.2
+    assert (X_opt_mc[0][:, 0] >= -0.6 - 1e-9).all() and (X_opt_mc[0][:, 0] <= 1.5 + 1e-9).all()
