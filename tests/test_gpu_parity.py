@@ -357,3 +357,61 @@ def test_invalid_arguments_are_rejected(handle, dev):
     assert e.value.code == EINVAL
     with pytest.raises(ValueError):
         handle.posterior_acq(gd, w['cand'].float(), None, w['f_best'], 3)
+
+
+@pytest.mark.parametrize('n,d,m,B', [(128, 8, 257, 2), (128, 3, 64, 1), (72, 6, 1, 3), (41, 7, 33, 2), (8, 1, 31, 2), (1, 2, 5, 1),
+                                     (64, 3, 100000, 1), (24, 2, 4097, 5)])
+def test_k4_shape_sweep_both_paths_agree_with_oracle(handle, dev, n, d, m, B):
+    """Limits of the DMMA path (n = 128, d = 8), tile/tail handling (m not a multiple of 32, m = 1), the two-pass
+    per-GP best when one GP's candidates are split over many CTAs (B = 1, m = 100,000), and n = 1."""
+    rng = np.random.default_rng(1000 * n + d)
+    gps, cands, priors, fbs = [], [], [], []
+    for b in range(B):
+        X = rng.uniform(-1, 1, (n, d)) * rng.uniform(0.5, 3.0, d) + rng.uniform(-5, 5, d)
+        y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n) + 3.0
+        if n == 1:
+            # a single point has zero spread: the reference's normalisation would divide by zero; give it a pair instead
+            X = np.vstack([X, X + 0.5]); y = np.array([y[0], y[0] + 1.0])
+        theta = np.concatenate([rng.uniform(-0.3, 0.9, d), rng.uniform(-0.3, 0.3, 1), [0.5 * np.log(10.0 ** rng.uniform(-3, -2))]])
+        gps.append(O.make_gp(X, y, theta))
+        cands.append(X[rng.integers(0, X.shape[0], m)] + rng.uniform(-0.4, 0.4, (m, d)))
+        priors.append(rng.standard_normal(m) * 0.1)
+        fbs.append(float(y.min()))
+    cands, priors, fbs = np.stack(cands), np.stack(priors), np.array(fbs)
+    g = gp_to_device(gps, dev)
+    res = {}
+    for path in (api._lib.K4_DMMA, api._lib.K4_GENERIC):
+        handle.set_option('k4_path', path)
+        try:
+            res[path] = handle.posterior_acq(g, T(cands, dev), T(priors, dev), T(fbs, dev), 3)
+        finally:
+            handle.set_option('k4_path', 0)
+    for b in range(B):
+        mv, vv, sv = O.posterior_acq_vectorised(cands[b], gps[b], priors[b], fbs[b], 3)
+        f_mean, f_var = floors(gps[b], cands[b])
+        for path, out in res.items():
+            assert (np.abs(out['mean'][b].cpu().numpy() - mv) <= RTOL * np.abs(mv) + f_mean).all(), (path, 'mean')
+            assert (np.abs(out['var'][b].cpu().numpy() - vv) <= RTOL * np.abs(vv) + f_var).all(), (path, 'var')
+            sc = out['score'][b].cpu().numpy()
+            assert int(out['best_idx'][b]) == int(np.argmin(sc)) and float(out['best_score'][b]) == sc.min()
+        # the two CUDA paths (tensor-core triangular form vs scalar full quadratic form) agree with each other
+        a, c = res[api._lib.K4_DMMA], res[api._lib.K4_GENERIC]
+        assert (np.abs(a['var'][b].cpu().numpy() - c['var'][b].cpu().numpy()) <= RTOL * np.abs(vv) + 2 * f_var).all()
+
+
+def test_k3_larger_than_register_path_uses_generic(handle, dev):
+    """n = 150 > 128: gprto_nlml falls through to the shared-memory kernel; same answer as the oracle."""
+    rng = np.random.default_rng(77)
+    X = rng.uniform(-1, 1, (1, 150, 3)); y = np.sin(X.sum(-1)) + 0.05 * rng.standard_normal((1, 150))
+    thetas = workloads.sobol_theta_starts(3, 4)[None]
+    nz = handle.normalise(T(X, dev), T(y, dev))
+    nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(thetas, dev))
+    _, _, _, _, Xn, Yn = O.normalise(X[0], y[0].reshape(-1, 1))
+    for s in range(4):
+        try:
+            ref = O.nlml(thetas[0, s], Xn, Yn[:, 0])
+        except np.linalg.LinAlgError:
+            continue
+        t = O.truth_ld(Xn, Yn[:, 0], thetas[0, s], jitter=1e-8)['nll']
+        assert int(st[0, s]) == 0
+        assert abs(float(nll[0, s]) - t) <= max(10 * abs(ref - t), 1e-9 * abs(t))
