@@ -17,6 +17,9 @@
 //   K itself is never written to memory: each lane evaluates the SE-ARD entries of its own fragments.
 #pragma once
 #include "gprto_math.cuh"
+#ifdef K3_TIMING
+#include <cstdio>
+#endif
 
 namespace gprto {
 
@@ -95,6 +98,14 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
   }
 
   double logdet = 0.0, quad = 0.0;
+#ifdef K3_TIMING
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define K3_MARK(i) { const long long tn = clock64(); tk[i] += tn - tprev; tprev = tn; }
+#else
+#define K3_MARK(i)
+#endif
+  K3_MARK(0)
 
 #pragma unroll 1
   for (int kb = 0; kb < NT; ++kb) {
@@ -107,49 +118,72 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
       if (J == kb) *reinterpret_cast<double2*>(&buf[(8 * I + g) * LDP + 2 * t]) = make_double2(C0[s], C1[s]);
     }
     __syncthreads();
+    K3_MARK(1)
     // (2) diagonal tile by warp 0: lane l < 8 owns row l, lane 8 owns the right-hand side block y'_kb as a ninth row
-    // (so z_kb = L11^-1 y'_kb falls out of the same elimination); pivots travel by shuffle, 1/sqrt by rsqrt_fast
+    // (so z_kb = L11^-1 y'_kb falls out of the same elimination).  The n-long pivot chain is the latency bottleneck of
+    // the whole kernel, so the elimination is DIVISION- AND SQRT-FREE: step c forms
+    //     a_jk <- d~ a_jk - (a_jc 2^-e) a_kc,   d~ = d 2^-e in [1,2),  e = exponent(d),  d = current (scaled) pivot,
+    // i.e. the Schur complement times d~ (a power-of-two normalised fraction-free step; the accumulated scale
+    // S_c = prod_{c'<c} d~_c' stays below 2^8).  The eight 1/sqrt are then independent:  L_jc = a'_jc rsqrt(d'_c S_c),
+    // one per lane, in parallel, after the chain (chain per column: shuffle, 3 integer ops, multiply, shuffle, FMA).
+    // Layout: the tile is spread over the warp like a DMMA accumulator (lane 4r+q holds a[r][2q], a[r][2q+1]) and the
+    // right-hand side block sits on lanes 0..7, so a column step is 6 shuffles + 6 FP64 instructions per lane instead
+    // of a 7-long serial loop per row.
     if (w == 0) {
-      const int l = lane < 9 ? lane : 0;
-      double dg[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) dg[c] = l < 8 ? buf[(8 * kb + l) * LDP + c] : ys[8 * kb + c];
-      double mypiv = 1.0, myr = 0.0;
+      const int r = lane >> 2, q = lane & 3, k8 = lane & 7;
+      const double2 v = *reinterpret_cast<const double2*>(&buf[(8 * kb + r) * LDP + 2 * q]);
+      double x0 = v.x, x1 = v.y;
+      double yv = ys[8 * kb + k8];
+      double S = 1.0, myS = 1.0, mydp = 1.0;
       int info = 0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const double piv = __shfl_sync(0xffffffffu, dg[c], c);
-        if (!(piv > 0.0) && info == 0) info = 8 * kb + c + 1;
-        const double r = rsqrt_fast(piv);
-        if (l == c) { mypiv = piv; myr = r; }
-        dg[c] = (l == c) ? piv * r : dg[c] * r;
-#pragma unroll
-        for (int j = c + 1; j < 8; ++j) {
-          const double ljc = __shfl_sync(0xffffffffu, dg[c], j);
-          dg[j] = fma(-dg[c], ljc, dg[j]);
-        }
+        const int cs = c >> 1;
+        const double colsel = (c & 1) ? x1 : x0;                                   // column c of my row (valid where q == cs)
+        const double dpiv = __shfl_sync(0xffffffffu, colsel, 4 * c + cs);          // a[c][c]
+        const double arc = __shfl_sync(0xffffffffu, colsel, 4 * r + cs);           // a[r][c]
+        const double ak0 = __shfl_sync(0xffffffffu, colsel, 4 * (2 * q) + cs);     // a[2q][c]
+        const double ak1 = __shfl_sync(0xffffffffu, colsel, 4 * (2 * q + 1) + cs); // a[2q+1][c]
+        const double ayk = __shfl_sync(0xffffffffu, colsel, 4 * k8 + cs);          // a[k8][c]
+        const double yc = __shfl_sync(0xffffffffu, yv, c);
+        if (!(dpiv > 0.0) && info == 0) info = 8 * kb + c + 1;
+        if (lane == c) { myS = S; mydp = dpiv; }
+        const int e = ((__double2hiint(dpiv) >> 20) & 0x7ff) - 1023;
+        const double f = __hiloint2double((1023 - e) << 20, 0);                    // 2^-e, exact
+        const double dt = dpiv * f;
+        const double ac = arc * f, ycf = yc * f;
+        const double n0 = fma(-ac, ak0, dt * x0), n1 = fma(-ac, ak1, dt * x1);
+        const double ny = fma(-ycf, ayk, dt * yv);
+        x0 = (2 * q > c) ? n0 : x0;                                                // columns <= c are final (frozen at scale S_col)
+        x1 = (2 * q + 1 > c) ? n1 : x1;
+        yv = (k8 > c) ? ny : yv;
+        S *= dt;
       }
-      double lg = 0.0;
+      const double tmine = lane < 8 ? rsqrt_fast(mydp * myS) : 1.0;                // lane c: rsqrt(d'_c S_c)
+      const double t0 = __shfl_sync(0xffffffffu, tmine, 2 * q), t1 = __shfl_sync(0xffffffffu, tmine, 2 * q + 1);
+      *reinterpret_cast<double2*>(&buf[(8 * kb + r) * LDP + 2 * q]) = make_double2(x0 * t0, x1 * t1);
+      double zq = 0.0, lg = 0.0;
       if (lane < 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) buf[(8 * kb + l) * LDP + c] = dg[c];
-        rinv_s[l] = myr;
-        lg = log(mypiv);
-      } else if (lane == 8) {
-        double q = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { zs[c] = dg[c]; q = fma(dg[c], dg[c], q); }
-        zs[8] = q;
+        const double z = yv * tmine;
+        zs[lane] = z;
+        zq = z * z;
+        rinv_s[lane] = tmine * myS;                                                // 1/L_cc = rsqrt(d'_c / S_c)
+        lg = 2.0 * log(mydp * tmine);                                              // log pivot = 2 log L_cc
       }
-      lg += __shfl_xor_sync(0xffffffffu, lg, 1);
-      lg += __shfl_xor_sync(0xffffffffu, lg, 2);
-      lg += __shfl_xor_sync(0xffffffffu, lg, 4);
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        lg += __shfl_xor_sync(0xffffffffu, lg, off);
+        zq += __shfl_xor_sync(0xffffffffu, zq, off);
+      }
       if (lane == 0) {
         logdet += lg;
+        zs[8] = zq;
         if (info != 0) s_info = info;
       }
     }
+    K3_MARK(2)
     __syncthreads();
+    K3_MARK(5)
     if (s_info != 0) break;
     // (3) panel rows (L21 = A21 L11^-T), one thread per remaining row
     {
@@ -175,6 +209,7 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
       if (tid == 0) quad += zs[8];
     }
     __syncthreads();
+    K3_MARK(3)
     // (4) trailing update with the FP64 tensor pipe
     double aA[2], aB[2];
 #pragma unroll
@@ -182,6 +217,42 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
       aA[s] = buf[(8 * rowA + g) * LDP + 4 * s + t];
       aB[s] = buf[(8 * rowB + g) * LDP + 4 * s + t];
     }
+#ifdef K3_BRANCHFREE_UPDATE
+    // (measured slower: 4.7e6 vs 6.1e6 evals/s at n=128 - the extra DMMAs of the co-resident CTA delay the FP64
+    // instructions on the pivot chain, which share the pipe)  Branch-free: every slot issues its two DMMAs each step; finished tiles (J <= kb) get a zero B operand, which
+    // leaves their (already spilled, never read again) accumulators unchanged.  Twice the DMMA count at the end of the
+    // factorisation, but no BSSY/BSYNC per tile, so the scheduler can hoist all fragment loads ahead of the MMAs -
+    // this phase is latency-bound (2 warps per scheduler), not pipe-bound.
+    double bq0[SLOTS], bq1[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int J = (s <= w) ? s : s - w - 1;
+      const double l0 = buf[(8 * J + g) * LDP + t], l1 = buf[(8 * J + g) * LDP + 4 + t];
+      bq0[s] = J > kb ? -l0 : 0.0;
+      bq1[s] = J > kb ? -l1 : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) dmma884(C0[s], C1[s], (s <= w) ? aA[0] : aB[0], bq0[s]);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) dmma884(C0[s], C1[s], (s <= w) ? aA[1] : aB[1], bq1[s]);
+    {
+      // y'_J -= L(J,kb) z_kb on the warp holding diagonal tile (J,J): slot w (row A) and slot NT (row B)
+      const int Jb = rowB;                       // slot NT: (rowB, rowB)
+      double pb = fma(bq0[NT], zs[t], bq1[NT] * zs[4 + t]);
+      double pa = 0.0;
+#pragma unroll
+      for (int s = 0; s < SLOTS - 1; ++s)
+        if (s == w) pa = fma(bq0[s], zs[t], bq1[s] * zs[4 + t]);   // slot w: (rowA, rowA); zero operand once finished
+      pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+      pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+      pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+      pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+      if (t == 0) {
+        if (rowA > kb) ys[8 * rowA + g] += pa;
+        if (Jb > kb) ys[8 * Jb + g] += pb;
+      }
+    }
+#else
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const int J = (s <= w) ? s : s - w - 1;
@@ -199,7 +270,12 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
         }
       }
     }
+#endif
+    K3_MARK(4)
   }
+#ifdef K3_TIMING
+  if (tid == 0 && (bs == 0 || bs == 20000)) printf("K3 timing block %lld: build %lld spill+bar %lld diag %lld (bar after diag %lld) panel+bar %lld update %lld cycles\n", (long long)bs, tk[0], tk[1], tk[2], tk[5], tk[3], tk[4]);
+#endif
 
   if (tid == 0) {
     const int info = s_info;
