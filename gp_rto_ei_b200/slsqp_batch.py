@@ -40,7 +40,8 @@ class Result(dict):
 
 
 def fd_steps(x0, lb, ub, eps=_EPS):
-    """Forward-difference steps of approx_derivative(method='2-point', abs_step=eps, bounds=(lb, ub))."""
+    """Forward-difference steps of approx_derivative(method='2-point', abs_step=eps, bounds=(lb, ub)); x0, lb, ub may
+    carry a leading batch axis."""
     h = np.full_like(x0, eps)
     dx = (x0 + h) - x0
     sign = (x0 >= 0).astype(float) * 2 - 1
@@ -51,12 +52,9 @@ def fd_steps(x0, lb, ub, eps=_EPS):
     x = x0 + h
     violated = (x < lb) | (x > ub)
     fitting = np.abs(h) <= np.maximum(lower, upper)
-    h = h.copy()
-    h[violated & fitting] *= -1
-    forward = (upper >= lower) & ~fitting
-    h[forward] = upper[forward]
-    backward = (upper < lower) & ~fitting
-    h[backward] = -lower[backward]
+    h = np.where(violated & fitting, -h, h)
+    h = np.where((upper >= lower) & ~fitting, upper, h)
+    h = np.where((upper < lower) & ~fitting, -lower, h)
     return h
 
 
@@ -104,44 +102,49 @@ def minimize_batch(fun_batch, x0s, bounds, con_batch=None, m_ineq=0, ftol=1e-6, 
         it.done = False
         insts.append(it)
 
+    LB, UB = np.asarray(lbs), np.asarray(ubs)
+    eye = np.eye(n)
+
     def evaluate(need_f, need_g):
-        """One batched round: f (and c) at the iterates of need_f, forward differences for need_g."""
-        ids, pts = [], []
-        for k in need_f:
-            ids.append(insts[k].idx); pts.append(np.clip(insts[k].x, lbs[k], ubs[k]))
-        steps = {}
-        for k in need_g:
-            it = insts[k]
-            xc = np.clip(it.x, lbs[k], ubs[k])
-            h = fd_steps(xc, lbs[k], ubs[k], eps)
-            steps[k] = (xc, h)
-            for i in range(n):
-                xp = xc.copy()
-                xp[i] = xc[i] + h[i]
-                ids.append(it.idx); pts.append(xp)
-        if not pts:
+        """One batched round: f (and c) at the iterates of need_f, forward differences for need_g.  All index and
+        step arithmetic is vectorised over the instances of the round (one NumPy call each, not one per instance)."""
+        need_f, need_g = list(need_f), list(need_g)
+        nf, ng_ = len(need_f), len(need_g)
+        if nf + ng_ == 0:
             return
-        ids = np.asarray(ids); P = np.asarray(pts)
+        blocks, ids = [], []
+        if nf:
+            Xf = np.clip(np.stack([insts[k].x for k in need_f]), LB[need_f], UB[need_f])
+            blocks.append(Xf)
+            ids.extend(insts[k].idx for k in need_f)
+        if ng_:
+            Xg = np.clip(np.stack([insts[k].x for k in need_g]), LB[need_g], UB[need_g])
+            H = fd_steps(Xg, LB[need_g], UB[need_g], eps)                      # [ng, n]
+            # point (k, i) = x_k + h_ki e_i ; the step actually taken is (x + h) - x  (approx_derivative does the same)
+            Pg = Xg[:, None, :] + H[:, :, None] * eye[None, :, :]            # [ng, n, n]
+            DX = (Xg + H) - Xg
+            blocks.append(Pg.reshape(ng_ * n, n))
+            for k in need_g:
+                ids.extend([insts[k].idx] * n)
+        ids = np.asarray(ids)
+        P = np.concatenate(blocks, axis=0)
         f = np.asarray(fun_batch(ids, P), dtype=float).reshape(-1)
-        c = np.asarray(con_batch(ids, P), dtype=float).reshape(len(pts), m) if m else None
-        pos = 0
-        for k in need_f:
+        c = np.asarray(con_batch(ids, P), dtype=float).reshape(P.shape[0], m) if m else None
+        for j, k in enumerate(need_f):
             it = insts[k]
-            it.fx = float(f[pos]); it.nfev += 1
+            it.fx = float(f[j]); it.nfev += 1
             if m:
-                it.d[:m] = c[pos]
-            pos += 1
-        for k in need_g:
-            it = insts[k]
-            xc, h = steps[k]
-            c0 = it.d[:m].copy() if m else None      # c(x0): same point, deterministic -> not re-evaluated
-            for i in range(n):
-                dx = (xc[i] + h[i]) - xc[i]
-                it.g[i] = (f[pos] - it.fx) / dx
+                it.d[:m] = c[j]
+        if ng_:
+            Fg = f[nf:].reshape(ng_, n)
+            Cg = c[nf:].reshape(ng_, n, m) if m else None
+            for j, k in enumerate(need_g):
+                it = insts[k]
+                it.g[:] = (Fg[j] - it.fx) / DX[j]
                 if m:
-                    it.C[:m, i] = (c[pos] - c0) / dx
-                pos += 1
-            it.nfev += n; it.njev += 1
+                    # c(x0) is the value stored at the last f/c evaluation of the same point (deterministic: not re-evaluated)
+                    it.C[:m, :] = ((Cg[j] - it.d[:m][None, :]) / DX[j][:, None]).T
+                it.nfev += n; it.njev += 1
 
     # mode 0 on entry: objective, constraints and both gradients at x0
     evaluate(range(K), range(K))

@@ -69,8 +69,10 @@ def _fit_group(handle, Xn_dev, Yn_dev_rows, bounds_rows, multi_start):
         Xb = Xn_dev.unsqueeze(0).expand(len(inst), n, d).contiguous()
         Yb = Yn_dev_rows.index_select(0, gsel).contiguous()
         nll, st = handle.nlml(Xb, Yb, _dev(P, handle).unsqueeze(1), jitter=_JITTER)
-        handle.raise_on_failure(st, 'negative_loglikelihood')          # numpy.linalg.LinAlgError as utilities_2.py:107
-        return nll.reshape(-1).cpu().numpy()
+        out = nll.reshape(-1).cpu().numpy()
+        if np.isnan(out).any():                                          # NaN <=> non-zero status: one D2H instead of two
+            handle.raise_on_failure(st, 'negative_loglikelihood')        # numpy.linalg.LinAlgError as utilities_2.py:107
+        return out
 
     res = slsqp_batch.minimize_batch(fun_batch, x0s, bnds, ftol=1e-12, maxiter=10000, inst_ids=list(range(len(x0s))))
     theta = np.empty((G, d + 2))

@@ -129,3 +129,15 @@ def test_run_main_executes_a_reference_style_driver(u2, tmp_path):
     f = S.Benoit_System_noiseless(np.asarray(xnew_mc[0]).flatten())
     assert 0.05 < f < 1.2
     assert (X_opt_mc[0][:, 0] >= -0.6 - 1e-9).all() and (X_opt_mc[0][:, 0] <= 1.5 + 1e-9).all()
+
+
+def test_replica_driver_is_reproducible_per_seed(u2):
+    """SURVEY.md par. 8f-2: replica r is a function of its seed alone (both RNGs seeded), whatever ran before it."""
+    from gp_rto_ei_b200 import replicas
+    kw = dict(problem='simple', obj_setting=3, n_iter=3, multi_opt=5, multi_hyper=3)
+    a = replicas.run_replica(3, **kw)
+    replicas.run_replica(1, **kw)
+    b = replicas.run_replica(3, **kw)
+    assert a == b and set(a) >= {'objective', 'feasible', 'x', 'seed'}
+    w = replicas.run_replica(0, problem='wo', obj_setting=3, n_iter=2, multi_opt=4, multi_hyper=3)
+    assert 4.0 <= w['x'][0] <= 7.0 and 70.0 <= w['x'][1] <= 100.0 and -200 < w['objective'] < 200   # -profit; the optimum is -75.8
