@@ -313,6 +313,30 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_best_value = float(Be) * m * world * e2e_steps / float(t[0])
+    # variant with on-device candidates (gprto_posterior_acq_sampled): per GP only (centre, radius) go in (H2D from pinned
+    # memory each step) and (best score, best index, best point) come back; full batch of B GPs
+    ctr_h = w['X'][:, 0, :].contiguous().cpu().pin_memory()
+    rad_h = torch.full((B,), 0.25, dtype=torch.float64).pin_memory()
+    ctr_d = torch.empty(B, d, dtype=torch.float64, device=dev); rad_d = torch.empty(B, dtype=torch.float64, device=dev)
+    so = dict(best_score=torch.empty(B, dtype=torch.float64, device=dev), best_idx=torch.empty(B, dtype=torch.int64, device=dev),
+              best_x=torch.empty(B, d, dtype=torch.float64, device=dev))
+    so_h = {k: torch.empty_like(v, device='cpu').pin_memory() for k, v in so.items()}
+
+    def sampled_step(seed):
+        ctr_d.copy_(ctr_h, non_blocking=True); rad_d.copy_(rad_h, non_blocking=True)
+        h.posterior_acq_sampled(gd, ctr_d, rad_d, m, shape=1, seed=seed, f_best=f_best, acq=3, out=so)
+        for k in so:
+            so_h[k].copy_(so[k], non_blocking=True)
+        torch.cuda.synchronize()
+    sampled_step(0)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        sampled_step(i + 1)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_sampled_value = float(B) * m * world * e2e_steps / float(t[0])
 
     if rank != 0:
         if world > 1:
@@ -364,7 +388,10 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'sample': 'gprto_posterior_acq_host on %d GPs x %d candidates per GPU, pinned host buffers, %d steps' % (Be, m, e2e_steps),
                 'best_only': {'value': e2e_best_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': Be * 16,
-                              'note': 'same call returning only the per-GP arg-min (what the RTO loop consumes)'}},
+                              'note': 'same call returning only the per-GP arg-min (what the RTO loop consumes)'},
+                'sampled_on_device': {'value': e2e_sampled_value, 'unit': UNIT, 'h2d_bytes_per_step': B * (d + 1) * 8, 'd2h_bytes_per_step': B * (d + 2) * 8,
+                                      'note': 'gprto_posterior_acq_sampled: the %d trust-region (ball) candidates of each of %d GPs are generated inside K4 from '
+                                              '(centre, radius, seed); returns best score / index / point per GP' % (m, B)}},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,

@@ -1,7 +1,7 @@
 """ctypes binding of libgprto.so (C ABI: include/gprto.h).  No fallback: a missing library is an error."""
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GPRTO_LIB', os.path.join(HERE, 'libgprto.so'))   # GPRTO_LIB: A/B builds of the same ABI
@@ -29,6 +29,8 @@ PROTOTYPES = {
     'gprto_factor': (c_int, [c_void_p, c_int64, c_int, c_int, _P, _P, _P, c_double, _P, _P, _P, _P, _P]),
     'gprto_posterior_acq': (c_int, [c_void_p, c_int64, c_int, c_int, c_int64] + [_P] * 11 + [c_int] + [_P] * 5 + [_P]),
     'gprto_posterior_acq_host': (c_int, [c_void_p, c_int64, c_int, c_int, c_int64] + [_P] * 11 + [c_int] + [_P] * 5),
+    'gprto_sample_candidates': (c_int, [c_void_p, c_int64, c_int, c_int64, _P, _P, c_int, c_uint64, _P, _P, _P]),
+    'gprto_posterior_acq_sampled': (c_int, [c_void_p, c_int64, c_int, c_int, c_int64] + [_P] * 10 + [c_int, c_uint64, _P, c_int, _P, _P, _P, _P]),
     'gprto_pack_best': (c_int, [c_void_p, c_int64, _P, _P, c_int64, _P, _P]),
     'gprto_first_failure': (c_int, [c_void_p, _P, c_int64, _P, POINTER(c_int64)]),
 }

@@ -168,6 +168,27 @@ class Handle:
             g('mean'), g('var'), g('score'), g('best_score'), g('best_idx')), 'gprto_posterior_acq_host')
         return out_host
 
+    def sample_candidates(self, centre, radius, m, shape=0, seed=0, idx=None):
+        """centre[B,d], radius[B] -> cand[B,m,d] (or [B,d] for the candidates idx[B])."""
+        B, d = centre.shape
+        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B,), 'radius')
+        out = self._new(B, d) if idx is not None else self._new(B, m, d)
+        _lib.check(self.lib.gprto_sample_candidates(self._h, B, d, m, _ptr(centre), _ptr(radius), int(shape), int(seed), _ptr(idx),
+                                                    _ptr(out), self._stream()), 'gprto_sample_candidates')
+        return out
+
+    def posterior_acq_sampled(self, gp, centre, radius, m, shape=0, seed=0, f_best=None, acq=ACQ_EI, out=None):
+        """K4 with the m candidates of each GP generated inside the kernel; returns best_score[B], best_idx[B], best_x[B,d]."""
+        B, n, d = gp['Xn'].shape
+        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B,), 'radius')
+        out = out or dict(best_score=self._new(B), best_idx=self._new(B, dtype=torch.int64), best_x=self._new(B, d))
+        _lib.check(self.lib.gprto_posterior_acq_sampled(
+            self._h, B, n, d, int(m), _ptr(gp['Xn']), _ptr(gp['invK']), _ptr(gp['alpha']), _ptr(gp['theta']), _ptr(gp['x_mean']),
+            _ptr(gp['x_std']), _ptr(gp['y_mean']), _ptr(gp['y_std']), _ptr(centre), _ptr(radius), int(shape), int(seed), _ptr(f_best),
+            int(acq), _ptr(out['best_score']), _ptr(out['best_idx']), _ptr(out.get('best_x')), self._stream()),
+            'gprto_posterior_acq_sampled')
+        return out
+
     def pack_best(self, best_score, best_idx, idx_offset=0, out=None):
         count = best_score.numel()
         rec = self._new(count, 2) if out is None else out

@@ -129,17 +129,20 @@ int posterior_device(gprto_t* h, int64_t B, int n, int d, int64_t m, const doubl
                      const double* alpha, const double* theta_opt, const double* x_mean, const double* x_std,
                      const double* y_mean, const double* y_std, const double* cand, const double* prior,
                      const double* f_best, int acq, double* mean, double* var, double* score, double* best_score,
-                     int64_t* best_idx, cudaStream_t s) {
+                     int64_t* best_idx, cudaStream_t s, const double* centre = nullptr, const double* radius = nullptr,
+                     int shape = 0, uint64_t seed = 0) {
   const bool dmma_ok = n <= K4_DMMA_MAXN && d <= K4_DMMA_MAXD;
   bool use_dmma = dmma_ok;
   if (h->k4_path == GPRTO_K4_GENERIC) use_dmma = false;
   if (h->k4_path == GPRTO_K4_DMMA && !dmma_ok) return GPRTO_EUNSUPPORTED;
   if (!use_dmma && (n > K4G_MAXN || d > K4G_MAXD)) return GPRTO_EUNSUPPORTED;
+  if (!cand && !use_dmma) return GPRTO_EUNSUPPORTED;      // fused sampling lives in the DMMA kernel only
   K4Params p{};
   p.B = B; p.m = m; p.n = n; p.d = d; p.acq = acq;
   p.Xn = Xn; p.invK = invK; p.alpha = alpha; p.theta = theta_opt; p.x_mean = x_mean; p.x_std = x_std;
   p.y_mean = y_mean; p.y_std = y_std; p.cand = cand; p.prior = prior; p.f_best = f_best;
   p.mean = mean; p.var = var; p.score = score;
+  p.centre = centre; p.radius = radius; p.shape = shape; p.seed = seed;
   // Chunking: one CTA per GP when the batch alone fills the machine, otherwise split the candidates of each GP
   // so that the grid has >= ~8 CTAs per SM.
   const int64_t gran = use_dmma ? K4_THREADS : K4G_THREADS;
@@ -202,6 +205,30 @@ int ensure_stage(gprto_t* h, size_t in_bytes, size_t out_bytes) {
     h->stage_out_cap = out_bytes;
   }
   return 0;
+}
+
+template <int D>
+int launch_sample(gprto_t* h, int64_t B, int64_t m, const double* centre, const double* radius, int shape, uint64_t seed,
+                         const int64_t* idx, double* out, cudaStream_t s) {
+  const int64_t total = idx ? B : B * m;
+  sample_candidates_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(B, m, centre, radius, shape, seed, idx, out);
+  h->launches++;
+  return launch_status();
+}
+
+int dispatch_sample(gprto_t* h, int64_t B, int d, int64_t m, const double* centre, const double* radius, int shape,
+                           uint64_t seed, const int64_t* idx, double* out, cudaStream_t s) {
+  switch (d) {
+    case 1: return launch_sample<1>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 2: return launch_sample<2>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 3: return launch_sample<3>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 4: return launch_sample<4>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 5: return launch_sample<5>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 6: return launch_sample<6>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 7: return launch_sample<7>(h, B, m, centre, radius, shape, seed, idx, out, s);
+    case 8: return launch_sample<8>(h, B, m, centre, radius, shape, seed, idx, out, s);
+  }
+  return GPRTO_EUNSUPPORTED;
 }
 
 }  // namespace
@@ -423,6 +450,31 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m, con
   GPRTO_CUDA(cudaStreamSynchronize(h->st[1]));
   GPRTO_CUDA(cudaStreamSynchronize(h->st[0]));
   return 0;
+}
+
+int gprto_sample_candidates(gprto_t* h, int64_t B, int d, int64_t m, const double* centre, const double* radius, int shape,
+                            uint64_t seed, const int64_t* idx, double* out, void* stream) {
+  if (!h || B <= 0 || d <= 0 || m <= 0 || !centre || !radius || !out || shape < 0 || shape > 1) return GPRTO_EINVAL;
+  DeviceGuard guard(h->device);
+  return dispatch_sample(h, B, d, m, centre, radius, shape, seed, idx, out, (cudaStream_t)stream);
+}
+
+int gprto_posterior_acq_sampled(gprto_t* h, int64_t B, int n, int d, int64_t m, const double* Xn, const double* invK,
+                                const double* alpha, const double* theta_opt, const double* x_mean, const double* x_std,
+                                const double* y_mean, const double* y_std, const double* centre, const double* radius, int shape,
+                                uint64_t seed, const double* f_best, int acq, double* best_score, int64_t* best_idx, double* best_x,
+                                void* stream) {
+  if (!h || B <= 0 || n <= 0 || d <= 0 || m <= 0 || !Xn || !invK || !alpha || !theta_opt || !x_mean || !x_std || !y_mean || !y_std ||
+      !centre || !radius || !best_score || !best_idx)
+    return GPRTO_EINVAL;
+  if (acq < 1 || acq > 3 || shape < 0 || shape > 1) return GPRTO_EINVAL;
+  if (acq == GPRTO_ACQ_EI && !f_best) return GPRTO_EINVAL;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = posterior_device(h, B, n, d, m, Xn, invK, alpha, theta_opt, x_mean, x_std, y_mean, y_std, nullptr, nullptr, f_best, acq,
+                            nullptr, nullptr, nullptr, best_score, best_idx, s, centre, radius, shape, seed);
+  if (rc || !best_x) return rc;
+  return dispatch_sample(h, B, d, m, centre, radius, shape, seed, best_idx, best_x, s);
 }
 
 int gprto_pack_best(gprto_t* h, int64_t count, const double* best_score, const int64_t* best_idx, int64_t idx_offset,

@@ -76,6 +76,49 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
   return y;
 }
 
+// Counter-based trust-region sampler shared by K4's fused mode and gprto_sample_candidates: candidate c of GP b is a
+// pure function of (seed, b, c).  shape 0: uniform in the box [-1,1]^D; shape 1: uniform in the unit ball (Gaussian
+// direction x U^(1/D)); the direction arithmetic is FP32 (SFU log/sin/cos) - it only has to be deterministic, the
+// resulting point is then used in full FP64 everywhere.  The caller maps u to centre + radius * u.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {      // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+template <int D>
+__device__ __forceinline__ void tr_sample(uint64_t seed, int64_t b, int64_t c, int shape, double (&u)[D]) {
+  const uint64_t key = mix64(seed ^ mix64(uint64_t(b) * 0xD1342543DE82EF95ULL + uint64_t(c)));
+  if (shape == 0) {
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) {
+      const uint64_t r = mix64(key + uint64_t(dd + 1));
+      u[dd] = double(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+  } else {
+    float z[D];
+    float n2 = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < D; dd += 2) {
+      const uint64_t r = mix64(key + uint64_t(dd + 1));
+      const float u1 = (float(uint32_t(r >> 40)) + 0.5f) * (1.0f / 16777216.0f);      // (0,1)
+      const float u2 = (float(uint32_t(r) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * __logf(u1));
+      float sn, cs;
+      __sincosf(6.283185307179586f * u2, &sn, &cs);
+      z[dd] = rad * cs;
+      n2 = fmaf(z[dd], z[dd], n2);
+      if (dd + 1 < D) { z[dd + 1] = rad * sn; n2 = fmaf(z[dd + 1], z[dd + 1], n2); }
+    }
+    const uint64_t r = mix64(key + uint64_t(D + 7));
+    const float ur = (float(uint32_t(r >> 40)) + 0.5f) * (1.0f / 16777216.0f);
+    const float scale = exp2f(__log2f(ur) * (1.0f / D)) * rsqrtf(n2);
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) u[dd] = double(z[dd] * scale);
+  }
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)

@@ -12,6 +12,10 @@ struct K4Params {
   int64_t chunk;       // candidates per CTA (multiple of 32*warps)
   int nchunks;         // CTAs per GP
   const double *Xn, *invK, *alpha, *theta, *x_mean, *x_std, *y_mean, *y_std, *cand, *prior, *f_best;
+  // fused sampling mode (cand == nullptr): candidate c of GP b = centre[b] + radius[b] * tr_sample(seed, b, c)
+  const double *centre, *radius;
+  uint64_t seed;
+  int shape;
   double *mean, *var, *score;
   double* part_score;  // [B, nchunks] partial arg-min (nullptr if best not requested)
   int64_t* part_idx;
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
 
   const int64_t c_begin = int64_t(blockIdx.y) * p.chunk;
   const int64_t c_end = min(p.m, c_begin + p.chunk);
-  const double* cand = p.cand + b * p.m * D;
+  const double* cand = p.cand ? p.cand + b * p.m * D : nullptr;
   const double* Xt = Xs + 2 * t * D;       // + (8*(s>>1) + (s&1))*D + dd   (compile-time offsets)
   const double* At = As + 2 * t;
   const double* Mlane = Mf + lane;
@@ -118,8 +122,16 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
     const int64_t ce = base + 8 * t + g;          // the candidate this lane finishes in the epilogue
     const bool valid = ce < c_end;
     double xe[D];
+    if (cand) {
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (cand[ce * D + dd] - mu_d[dd]) * a_d[dd] : 0.0;
+      for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (cand[ce * D + dd] - mu_d[dd]) * a_d[dd] : 0.0;
+    } else {
+      double u[D];
+      tr_sample<D>(p.seed, b, ce, p.shape, u);
+      const double rad = p.radius[b];
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (fma(rad, u[dd], p.centre[b * D + dd]) - mu_d[dd]) * a_d[dd] : 0.0;
+    }
 
     double q_mine = 0.0, m_mine = 0.0;
 #pragma unroll 1
@@ -274,6 +286,22 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
       p.part_idx[b * p.nchunks + blockIdx.y] = best_i;
     }
   }
+}
+
+// Materialise the sampler's candidates (same function as K4's fused mode): cand[b, c, :] = centre[b] + radius[b] * u.
+// With idx != nullptr only candidate idx[b] of each GP is produced (out[b, :]) - the coordinates of the per-GP best.
+template <int D>
+__global__ void sample_candidates_kernel(int64_t B, int64_t m, const double* __restrict__ centre, const double* __restrict__ radius,
+                                         int shape, uint64_t seed, const int64_t* __restrict__ idx, double* __restrict__ out) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = idx ? B : B * m;
+  if (e >= total) return;
+  const int64_t b = idx ? e : e / m;
+  const int64_t c = idx ? idx[e] : e - b * m;
+  double u[D];
+  tr_sample<D>(seed, b, c, shape, u);
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) out[e * D + dd] = fma(radius[b], u[dd], centre[b * D + dd]);
 }
 
 // Row-wise arg-min (numpy.argmin semantics) - also the second pass of K4's per-GP best and the

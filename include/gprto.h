@@ -114,6 +114,22 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m,
                              double* mean_host, double* var_host, double* score_host,
                              double* best_score_host, int64_t* best_idx_host);
 
+/* On-device trust-region candidates (SURVEY.md par. 8f-4; the reference draws its start points on the host,
+ * utilities_2.py:678-730).  Candidate c of GP b is a pure function of (seed, b, c):
+ *   cand[b,c,:] = centre[b,:] + radius[b] * u,   u uniform in [-1,1]^d (shape 0) or in the unit ball (shape 1).
+ * gprto_sample_candidates materialises them: out[B,m,d], or, with idx[B] != NULL, only candidate idx[b] of each GP
+ * (out[B,d]).  gprto_posterior_acq_sampled is K4 with the SAME candidates generated inside the kernel (no candidate
+ * array in memory at all); it returns the per-GP arg-min (best_score[B], best_idx[B]) and, if best_x != NULL, the
+ * coordinates best_x[B,d] of the winning candidates.  prior is not available in this mode. */
+int gprto_sample_candidates(gprto_t* h, int64_t B, int d, int64_t m, const double* centre, const double* radius, int shape,
+                            uint64_t seed, const int64_t* idx, double* out, void* stream);
+int gprto_posterior_acq_sampled(gprto_t* h, int64_t B, int n, int d, int64_t m,
+                                const double* Xn, const double* invK, const double* alpha, const double* theta_opt,
+                                const double* x_mean, const double* x_std, const double* y_mean, const double* y_std,
+                                const double* centre, const double* radius, int shape, uint64_t seed,
+                                const double* f_best, int acq, double* best_score, int64_t* best_idx, double* best_x,
+                                void* stream);
+
 /* Pack (score, index) pairs as 16-byte records {double score; int64 idx + idx_offset} into `out[count]`:
  * the send buffer of the final NCCL all-gather. */
 int gprto_pack_best(gprto_t* h, int64_t count, const double* best_score, const int64_t* best_idx,

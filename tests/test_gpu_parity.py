@@ -415,3 +415,30 @@ def test_k3_larger_than_register_path_uses_generic(handle, dev):
         t = O.truth_ld(Xn, Yn[:, 0], thetas[0, s], jitter=1e-8)['nll']
         assert int(st[0, s]) == 0
         assert abs(float(nll[0, s]) - t) <= max(10 * abs(ref - t), 1e-9 * abs(t))
+
+
+@pytest.mark.parametrize('shape', [0, 1])
+def test_fused_sampling_matches_materialised_candidates(handle, dev, shape):
+    """SURVEY.md par. 8f-4: K4 with candidates generated inside the kernel gives bit-identical per-GP results to K4 on the
+    same candidates materialised by gprto_sample_candidates; the sampler is uniform in the box / ball and seed-stable."""
+    w = workloads.cfg3_torch(dev, seed=21, B=64, n=64, d=3, m=8)
+    gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
+    centre = w['X'][:, 5, :].contiguous()
+    radius = torch.full((64,), 0.25, dtype=torch.float64, device=dev)
+    m = 5000
+    cand = handle.sample_candidates(centre, radius, m, shape=shape, seed=1234)
+    again = handle.sample_candidates(centre, radius, m, shape=shape, seed=1234)
+    other = handle.sample_candidates(centre, radius, m, shape=shape, seed=1235)
+    assert torch.equal(cand, again) and not torch.equal(cand, other)
+    u = (cand - centre[:, None, :]) / 0.25
+    if shape == 0:
+        assert float(u.abs().max()) <= 1.0 and abs(float(u.mean())) < 5e-3 and abs(float(u.var()) - 1.0 / 3.0) < 5e-3
+    else:
+        r = u.norm(dim=-1)
+        assert float(r.max()) <= 1.0 + 1e-6 and abs(float(u.mean())) < 5e-3
+        assert abs(float((r ** 3).mean()) - 0.5) < 5e-3                  # r^d is uniform for a uniform ball
+    ref = handle.posterior_acq(gd, cand, None, w['f_best'], 3, want=('score', 'best'))
+    out = handle.posterior_acq_sampled(gd, centre, radius, m, shape=shape, seed=1234, f_best=w['f_best'], acq=3)
+    assert torch.equal(out['best_idx'], ref['best_idx']) and torch.equal(out['best_score'], ref['best_score'])
+    bx = cand[torch.arange(64, device=dev), ref['best_idx']]
+    assert torch.equal(out['best_x'], bx)
