@@ -373,7 +373,9 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(REPO, 'profiles', 'k4_ncu_summary.json')) as fh_:
-            traffic = json.load(fh_).get('dram_bytes_per_launch')
+            j_ = json.load(fh_)
+            # ncu capture was taken on a slice of the batch (same kernel, same per-GP work): scale to this launch
+            traffic = j_['dram_bytes_per_launch'] * (float(B) * m) / (j_['gps_in_capture'] * j_['candidates_per_gp'])
     except Exception:
         pass
     line = {

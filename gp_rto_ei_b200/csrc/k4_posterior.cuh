@@ -21,6 +21,10 @@ struct K4Params {
   int64_t* part_idx;
 };
 
+#ifndef K4_UNROLL_U
+#define K4_UNROLL_U 1
+#endif
+constexpr int K4_UNROLL = K4_UNROLL_U;   // tiles of the 4-tile group processed together (ILP vs registers)
 constexpr int K4_WARPS = 4;
 constexpr int K4_THREADS = K4_WARPS * 32;
 #ifndef K4_MINB
@@ -115,6 +119,9 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
   const double* At = As + 2 * t;
   const double* Mlane = Mf + lane;
 
+#ifdef K4_EXP_TABLE
+  const double exp_tv = exp2(double(lane) * (1.0 / 32.0));      // lane l: 2^(l/32)
+#endif
   double best_v = CUDART_INF;
   int64_t best_i = INT64_MAX;
 
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
     }
 
     double q_mine = 0.0, m_mine = 0.0;
-#pragma unroll 1
+#pragma unroll K4_UNROLL
     for (int u = 0; u < 4; ++u) {
       double x[D];
 #pragma unroll
@@ -151,7 +158,11 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
           const double df = x[dd] - Xt[(8 * (s >> 1) + (s & 1)) * D + dd];
           acc = fma(df * df, nhw[dd], acc);
         }
+#ifdef K4_EXP_TABLE
+        kv[s] = exp_fast_tab(acc, exp_tv);
+#else
         kv[s] = exp_fast(acc);
+#endif
       }
       double C0[NB], C1[NB];
 #pragma unroll
