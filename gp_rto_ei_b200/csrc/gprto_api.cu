@@ -12,6 +12,7 @@
 
 #include "k23_chol.cuh"
 #include "k3_nlml_reg.cuh"
+#include "k3_nlml_la.cuh"
 #include "k4_posterior.cuh"
 
 using namespace gprto;
@@ -299,7 +300,7 @@ int gprto_destroy(gprto_t* h) {
 int gprto_set_option(gprto_t* h, const char* name, int64_t value) {
   if (!h || !name) return GPRTO_EINVAL;
   if (!strcmp(name, "k4_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k4_path = int(value); return 0; }
-  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 1) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
+  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
   return GPRTO_EINVAL;
 }
 
@@ -334,8 +335,10 @@ int gprto_nlml(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, con
   if (d > CH_MAXD) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->k3_path == 0 && n <= K3R_MAXN && d <= K3R_MAXD) {
-    int rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+  if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
+    int rc = GPRTO_EUNSUPPORTED;
+    if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);     // n > 48: look-ahead kernel
+    if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
     if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
   }
   const size_t smem = ch_smem_bytes(n, d);

@@ -52,7 +52,7 @@ const char* gprto_error_string(int code);
 /* limits[0] = max n of the DMMA posterior path, [1] = max n of the register-resident NLML path,
  * [2] = max n overall, [3] = max d. */
 int  gprto_limits(int64_t limits[4]);
-int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto,1 generic */
+int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead */
 /* Number of kernels this library launched through the handle since creation (bench.py's gpu_launches). */
 int64_t gprto_launch_count(const gprto_t* h);
 

@@ -213,7 +213,7 @@ def _check_nlml(handle, dev, X, y, thetas, ref, fail, label):
     """X[B,n,d], y[B,n], thetas[B,S,d+2]; ref[B,S]."""
     nz = handle.normalise(T(X, dev), T(y, dev))
     worst = 0.0
-    for k3 in (0, 1):
+    for k3 in (0, 1, 2):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(thetas, dev))
         handle.set_option('k3_path', 0)
@@ -262,7 +262,7 @@ def test_k3_status_flags_non_positive_definite(handle, dev):
     y = np.array([[1.0, 2.0, 0.5, -1.0]])
     nz = handle.normalise(T(X, dev), T(y, dev))
     theta = np.array([[[0.0, 0.0, 0.0, -400.0], [0.0, 0.0, 0.0, -2.0]]])
-    for k3 in (0, 1):
+    for k3 in (0, 1, 2):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(theta, dev), jitter=0.0)
         handle.set_option('k3_path', 0)
