@@ -22,6 +22,7 @@ struct gprto_handle {
   int sm_count = 0;
   int k4_path = GPRTO_K4_AUTO;
   int k3_path = 0;
+  int cov_kernel_kind = 0;
   std::atomic<int64_t> launches{0};
   // scratch (grown on demand)
   double* part_score = nullptr;
@@ -300,6 +301,7 @@ int gprto_destroy(gprto_t* h) {
 int gprto_set_option(gprto_t* h, const char* name, int64_t value) {
   if (!h || !name) return GPRTO_EINVAL;
   if (!strcmp(name, "k4_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k4_path = int(value); return 0; }
+  if (!strcmp(name, "cov_kernel")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->cov_kernel_kind = int(value); return 0; }
   if (!strcmp(name, "k3_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
   return GPRTO_EINVAL;
 }
@@ -324,7 +326,7 @@ int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* X
   const size_t smem = (size_t(n) * d + CH_MAXD) * sizeof(double);
   int rc = set_smem(cov_kernel, smem);
   if (rc) return rc;
-  cov_kernel<<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, K);
+  cov_kernel<<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, h->cov_kernel_kind, K);
   h->launches++;
   return launch_status();
 }

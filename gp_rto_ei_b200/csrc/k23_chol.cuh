@@ -126,9 +126,11 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
 }
 
 // K1: Gram matrix to global memory (API parity with Cov_mat; the fused kernels never materialise K).
+// kind 0: SE-ARD (RBF branch, utilities_2.py:57-59); 1: Matern-3/2 (:61-63); 2: Matern-5/2 (:64-66), with
+// dist = sum (x - x')^2 / W and r = sqrt(dist) exactly as the reference forms them from cdist.
 __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, const double* __restrict__ Xn,
                                                          const double* __restrict__ theta_all, int add_noise,
-                                                         double jitter, double* __restrict__ K) {
+                                                         double jitter, int kind, double* __restrict__ K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Xs = reinterpret_cast<double*>(smem_raw);
   double* nhw = Xs + n * d;
@@ -139,16 +141,24 @@ __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, co
   __syncthreads();
   const double diag = (add_noise ? exp(2.0 * theta[d + 1]) : 0.0) + jitter;
   const double c0 = 2.0 * theta[d];
+  const double sf2 = exp(c0);
   double* Kout = K + bs * int64_t(n) * n;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     const int lo = min(i, j), hi = max(i, j);   // evaluate (hi, lo) so the matrix is exactly symmetric
-    double acc = c0;
+    double acc = 0.0;                           // -dist / 2
     for (int dd = 0; dd < d; ++dd) {
       const double df = Xs[hi * d + dd] - Xs[lo * d + dd];
       acc = fma(df * df, nhw[dd], acc);
     }
-    double v = exp_fast(acc);
+    double v;
+    if (kind == 0) {
+      v = exp_fast(c0 + acc);
+    } else {
+      const double dist = -2.0 * acc, r = sqrt(dist);
+      if (kind == 1) v = sf2 * (1.0 + 1.7320508075688772 * r) * exp(-1.7320508075688772 * r);
+      else v = sf2 * (1.0 + 2.23606797749979 * r + (5.0 / 3.0) * dist) * exp(-2.23606797749979 * r);
+    }
     if (i == j) v += diag;
     Kout[e] = v;
   }

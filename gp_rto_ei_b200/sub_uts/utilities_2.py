@@ -113,12 +113,17 @@ class GP_model:
         return np.concatenate([0.5 * np.log(np.asarray(W, dtype=float).reshape(-1)), [0.5 * np.log(sf2)], [0.5 * np.log(sn2)]])
 
     def Cov_mat(self, kernel, X_norm, W, sf2):
-        if kernel != 'RBF':
+        kinds = {'RBF': 0, 'Matern32': 1, 'Matern52': 2}
+        if kernel not in kinds:
             print('ERROR no kernel with name ', kernel)          # the reference prints and returns None (:67-68)
             return None
         Xd = self._Xn if X_norm is self.X_norm else _dev(X_norm, self._h)
         th = _dev(self._theta_from(W, sf2), self._h).reshape(1, 1, -1)
-        return self._h.cov_se_ard(Xd.unsqueeze(0).contiguous(), th)[0, 0].cpu().numpy()
+        self._h.set_option('cov_kernel', kinds[kernel])
+        try:
+            return self._h.cov_se_ard(Xd.unsqueeze(0).contiguous(), th)[0, 0].cpu().numpy()
+        finally:
+            self._h.set_option('cov_kernel', 0)
 
     def calc_cov_sample(self, xnorm, Xnorm, ell, sf2):
         """k(x*, X) as an (n, 1) column - one row block of the Gram matrix of [X; x*]."""
@@ -286,7 +291,7 @@ class ITR_GP_RTO:
         ytrain = np.zeros((self.ng + 1, ndata))
         for ii in range(self.ng + 1):
             for i in range(ndata):
-                ytrain[ii, i] = sys_f[ii](np.array(Xtrain[i, :])) - mod_f[ii](np.array(Xtrain[i, :]))
+                ytrain[ii, i] = np.asarray(sys_f[ii](np.array(Xtrain[i, :])) - mod_f[ii](np.array(Xtrain[i, :]))).reshape(-1)[0]
         return Xtrain.reshape(ndata, ndim, order='F'), ytrain.reshape(self.ng + 1, ndata, order='F')
 
     # ---- scalar acquisition (utilities_2.py:477-507): kept for API parity; the optimiser uses the batched twin below
@@ -431,7 +436,7 @@ class ITR_GP_RTO:
         def mismatch_row(x):
             row = np.zeros((1, ng + 1))
             for ii in range(ng + 1):
-                row[0, ii] = sys_f[ii](np.array(x[:]).flatten()) - mod_f[ii](np.array(x[:]).flatten())
+                row[0, ii] = np.asarray(sys_f[ii](np.array(x[:]).flatten()) - mod_f[ii](np.array(x[:]).flatten())).reshape(-1)[0]
             return row
 
         xnew = self.x0

@@ -52,7 +52,8 @@ const char* gprto_error_string(int code);
 /* limits[0] = max n of the DMMA posterior path, [1] = max n of the register-resident NLML path,
  * [2] = max n overall, [3] = max d. */
 int  gprto_limits(int64_t limits[4]);
-int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead */
+int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead;
+                                                                         "cov_kernel": kernel of gprto_cov_se_ard only: 0 SE-ARD, 1 Matern-3/2, 2 Matern-5/2 */
 /* Number of kernels this library launched through the handle since creation (bench.py's gpu_launches). */
 int64_t gprto_launch_count(const gprto_t* h);
 
@@ -63,7 +64,9 @@ int gprto_normalise(gprto_t* h, int64_t B, int n, int d, const double* X, const 
                     double* Xn, double* Yn, void* stream);
 
 /* K1 - SE-ARD Gram matrix (replaces GP_model.Cov_mat, RBF branch, utilities_2.py:50-59, and the diagonal
- * terms of :105 / :173).  K[b,s] = sf2*exp(-0.5*dist) + (add_noise ? sn2 : 0)*I + jitter*I.
+ * terms of :105 / :173).  K[b,s] = sf2*exp(-0.5*dist) + (add_noise ? sn2 : 0)*I + jitter*I.  With option
+ * "cov_kernel" = 1 / 2 the Matern-3/2 / -5/2 forms of :61-66 are produced instead (never requested by the reference's
+ * drivers and not used by its inference, which is hard-wired to the SE kernel, :83).
  * Xn[B,n,d], theta[B,S,d+2] -> K[B,S,n,n] (full symmetric matrix). */
 int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, const double* theta,
                      int add_noise, double jitter, double* K, void* stream);

@@ -55,6 +55,11 @@ def test_gp_model_inference_api(u2):
     assert isinstance(gp.GP_inference_np(g[f'cand{i}'][0]), float)
     K = gp.Cov_mat('RBF', gp.X_norm, np.exp(2 * gp.hypopt[:2, 0]), np.exp(2 * gp.hypopt[2, 0]))
     assert np.abs(K - g[f'K{i}']).max() <= 1e-12 * g[f'K{i}'].max()
+    for kern in ('Matern32', 'Matern52'):            # selectable in the reference's Cov_mat (:61-66)
+        Km = gp.Cov_mat(kern, gp.X_norm, np.exp(2 * gp.hypopt[:2, 0]), np.exp(2 * gp.hypopt[2, 0]))
+        Ko = O.cov_mat(kern, gp.X_norm, np.exp(2 * gp.hypopt[:2, 0]), np.exp(2 * gp.hypopt[2, 0]))
+        assert np.abs(Km - Ko).max() <= 1e-12 * Ko.max()
+    assert gp.Cov_mat('nonsense', gp.X_norm, np.ones(2), 1.0) is None
     k = gp.calc_cov_sample((g[f'cand{i}'][0] - gp.X_mean) / gp.X_std, gp.X_norm, np.exp(2 * gp.hypopt[:2, 0]), np.exp(2 * gp.hypopt[2, 0]))
     assert k.shape == (X.shape[0], 1)
     assert np.allclose(k, O.cov_sample((g[f'cand{i}'][0] - gp.X_mean) / gp.X_std, gp.X_norm, np.exp(2 * gp.hypopt[:2, 0]), np.exp(2 * gp.hypopt[2, 0])), rtol=1e-12)

@@ -442,3 +442,22 @@ def test_fused_sampling_matches_materialised_candidates(handle, dev, shape):
     assert torch.equal(out['best_idx'], ref['best_idx']) and torch.equal(out['best_score'], ref['best_score'])
     bx = cand[torch.arange(64, device=dev), ref['best_idx']]
     assert torch.equal(out['best_x'], bx)
+
+
+def test_posterior_mean_is_linear_in_the_observations(handle, dev):
+    """Size-independent property at a BASELINE-sized n: with fixed hyper-parameters the normalised posterior mean is
+    linear in y and the variance does not depend on y at all (K2 + K4, 256 GPs x 1024 candidates, n = 64)."""
+    w = workloads.cfg3_torch(dev, seed=31, B=256, n=64, d=3, m=1024)
+    y2 = torch.cos(w['X'].sum(-1) * 1.7)
+    a, b = 0.7, -1.3
+    res = []
+    for y in (w['y'], y2, a * w['y'] + b * y2):
+        nz = handle.normalise(w['X'], y.contiguous())
+        invK, alpha, _, st = handle.factor(nz['Xn'], y.contiguous(), w['theta'])         # un-normalised targets on purpose
+        one, zero = torch.ones(256, dtype=torch.float64, device=dev), torch.zeros(256, dtype=torch.float64, device=dev)
+        gp = dict(Xn=nz['Xn'], invK=invK, alpha=alpha, theta=w['theta'], x_mean=nz['x_mean'], x_std=nz['x_std'], y_mean=zero, y_std=one)
+        res.append(handle.posterior_acq(gp, w['cand'], None, None, 1, want=('mean', 'var')))
+    lin = a * res[0]['mean'] + b * res[1]['mean']
+    scale = float(res[0]['mean'].abs().max() + res[1]['mean'].abs().max())
+    assert float((res[2]['mean'] - lin).abs().max()) < 1e-9 * scale
+    assert torch.equal(res[0]['var'], res[1]['var']) and torch.equal(res[0]['var'], res[2]['var'])
