@@ -25,6 +25,7 @@ PROTOTYPES = {
     'gprto_normalise': (c_int, [c_void_p, c_int64, c_int, c_int] + [_P] * 8 + [_P]),
     'gprto_cov_se_ard': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, _P, _P, c_int, c_double, _P, _P]),
     'gprto_nlml': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, _P, _P, _P, c_double, _P, _P, _P]),
+    'gprto_nlml_indexed_host': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, c_double, _P, _P]),
     'gprto_argmin': (c_int, [c_void_p, c_int64, c_int64, _P, _P, _P, _P]),
     'gprto_factor': (c_int, [c_void_p, c_int64, c_int, c_int, _P, _P, _P, c_double, _P, _P, _P, _P, _P]),
     'gprto_posterior_acq': (c_int, [c_void_p, c_int64, c_int, c_int, c_int64] + [_P] * 11 + [c_int] + [_P] * 5 + [_P]),

@@ -97,6 +97,36 @@ class Handle:
                                        self._stream()), 'gprto_nlml')
         return nll, st
 
+    def nlml_indexed_host(self, Xn, Yn, gp_index, theta, jitter=JITTER_NLML):
+        """Small synchronous batches driven from the host: Xn[G,n,d], Yn[G,n] on the device; gp_index[k] (int32) and
+        theta[k,d+2] NumPy arrays -> (nll[k], status[k]) NumPy arrays.  No torch objects are created on this path."""
+        G, n, d = Xn.shape
+        gp_index = np.ascontiguousarray(gp_index, dtype=np.int32)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        k = gp_index.shape[0]
+        nll = np.empty(k, dtype=np.float64)
+        st = np.empty(k, dtype=np.int32)
+        _lib.check(self.lib.gprto_nlml_indexed_host(self._h, G, k, n, d, _ptr(Xn), _ptr(Yn), gp_index.ctypes.data, theta.ctypes.data,
+                                                    float(jitter), nll.ctypes.data, st.ctypes.data), 'gprto_nlml_indexed_host')
+        return nll, st
+
+    def posterior_acq_host_np(self, gp, cand, prior=None, f_best=None, acq=ACQ_EI, want=('score',)):
+        """gprto_posterior_acq_host with NumPy arrays for the per-candidate streams: cand[B,m,d] (+ prior[B,m]) in,
+        dict of NumPy arrays out (keys of `want` among mean, var, score, best)."""
+        B, n, d = gp['Xn'].shape
+        cand = np.ascontiguousarray(cand, dtype=np.float64)
+        m = cand.shape[1]
+        prior = None if prior is None else np.ascontiguousarray(prior, dtype=np.float64)
+        out = {k: np.empty((B, m)) for k in ('mean', 'var', 'score') if k in want}
+        if 'best' in want:
+            out['best_score'], out['best_idx'] = np.empty(B), np.empty(B, dtype=np.int64)
+        g = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        _lib.check(self.lib.gprto_posterior_acq_host(
+            self._h, B, n, d, m, _ptr(gp['Xn']), _ptr(gp['invK']), _ptr(gp['alpha']), _ptr(gp['theta']), _ptr(gp['x_mean']),
+            _ptr(gp['x_std']), _ptr(gp['y_mean']), _ptr(gp['y_std']), cand.ctypes.data, None if prior is None else prior.ctypes.data,
+            _ptr(f_best), int(acq), g('mean'), g('var'), g('score'), g('best_score'), g('best_idx')), 'gprto_posterior_acq_host')
+        return out
+
     def argmin(self, val):
         B, S = val.shape
         self._chk(val, (B, S), 'val')

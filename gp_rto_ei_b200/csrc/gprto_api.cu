@@ -37,6 +37,11 @@ struct gprto_handle {
   double* dev_in[2] = {nullptr, nullptr};
   double* dev_out[2] = {nullptr, nullptr};
   size_t stage_in_cap = 0, stage_out_cap = 0;
+  // small synchronous host calls (gprto_nlml_indexed_host): one pinned + one device arena
+  unsigned char* small_pin = nullptr;
+  unsigned char* small_dev = nullptr;
+  size_t small_cap = 0;
+  cudaStream_t small_stream = nullptr;
 };
 
 namespace {
@@ -233,6 +238,23 @@ int dispatch_sample(gprto_t* h, int64_t B, int d, int64_t m, const double* centr
   return GPRTO_EUNSUPPORTED;
 }
 
+int nlml_device(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
+                double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
+  if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
+    int rc = GPRTO_EUNSUPPORTED;
+    if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead kernel
+    if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
+  }
+  const size_t smem = ch_smem_bytes(n, d);
+  if (smem > 227 * 1024) return GPRTO_EUNSUPPORTED;
+  int rc = set_smem(nlml_generic_kernel, smem);
+  if (rc) return rc;
+  nlml_generic_kernel<<<(unsigned)(B * S), CH_THREADS, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
+  h->launches++;
+  return launch_status();
+}
+
 }  // namespace
 
 extern "C" {
@@ -285,6 +307,9 @@ int gprto_destroy(gprto_t* h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   cudaFree(h->part_score); cudaFree(h->part_idx); cudaFree(h->first_dev);
+  if (h->small_pin) cudaFreeHost(h->small_pin);
+  cudaFree(h->small_dev);
+  if (h->small_stream) cudaStreamDestroy(h->small_stream);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
     if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
@@ -336,20 +361,44 @@ int gprto_nlml(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, con
   if (!h || B <= 0 || S <= 0 || n <= 0 || d <= 0 || !Xn || !Yn || !theta || !nll || !status) return GPRTO_EINVAL;
   if (d > CH_MAXD) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
-    int rc = GPRTO_EUNSUPPORTED;
-    if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);     // n > 48: look-ahead kernel
-    if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
+  return nlml_device(h, B, S, n, d, Xn, Yn, theta, jitter, nll, status, (cudaStream_t)stream, nullptr);
+}
+
+int gprto_nlml_indexed_host(gprto_t* h, int64_t G, int64_t k, int n, int d, const double* Xn, const double* Yn,
+                            const int32_t* gp_index_host, const double* theta_host, double jitter, double* nll_host,
+                            int32_t* status_host) {
+  if (!h || G <= 0 || k <= 0 || n <= 0 || d <= 0 || !Xn || !Yn || !gp_index_host || !theta_host || !nll_host || !status_host)
+    return GPRTO_EINVAL;
+  if (d > CH_MAXD) return GPRTO_EUNSUPPORTED;
+  for (int64_t i = 0; i < k; ++i)
+    if (gp_index_host[i] < 0 || gp_index_host[i] >= G) return GPRTO_EINVAL;
+  DeviceGuard guard(h->device);
+  // arena layout (both pinned and device): theta[k,d+2] | nll[k] | status[k] (int32) | index[k] (int32)
+  const size_t o_nll = size_t(k) * (d + 2) * 8, o_st = o_nll + size_t(k) * 8, o_idx = o_st + size_t(k) * 4, total = o_idx + size_t(k) * 4;
+  if (total > h->small_cap) {
+    if (h->small_pin) cudaFreeHost(h->small_pin);
+    if (h->small_dev) cudaFree(h->small_dev);
+    h->small_pin = nullptr; h->small_dev = nullptr; h->small_cap = 0;
+    const size_t cap = std::max<size_t>(total * 2, 1 << 16);
+    GPRTO_CUDA(cudaMallocHost(&h->small_pin, cap));
+    GPRTO_CUDA(cudaMalloc(&h->small_dev, cap));
+    h->small_cap = cap;
   }
-  const size_t smem = ch_smem_bytes(n, d);
-  if (smem > 227 * 1024) return GPRTO_EUNSUPPORTED;
-  int rc = set_smem(nlml_generic_kernel, smem);
+  if (!h->small_stream) GPRTO_CUDA(cudaStreamCreateWithFlags(&h->small_stream, cudaStreamNonBlocking));
+  cudaStream_t s = h->small_stream;
+  memcpy(h->small_pin, theta_host, o_nll);
+  memcpy(h->small_pin + o_idx, gp_index_host, size_t(k) * 4);
+  GPRTO_CUDA(cudaMemcpyAsync(h->small_dev, h->small_pin, o_nll, cudaMemcpyHostToDevice, s));
+  GPRTO_CUDA(cudaMemcpyAsync(h->small_dev + o_idx, h->small_pin + o_idx, size_t(k) * 4, cudaMemcpyHostToDevice, s));
+  int rc = nlml_device(h, k, 1, n, d, Xn, Yn, reinterpret_cast<const double*>(h->small_dev), jitter,
+                       reinterpret_cast<double*>(h->small_dev + o_nll), reinterpret_cast<int32_t*>(h->small_dev + o_st), s,
+                       reinterpret_cast<const int32_t*>(h->small_dev + o_idx));
   if (rc) return rc;
-  nlml_generic_kernel<<<(unsigned)(B * S), CH_THREADS, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status);
-  h->launches++;
-  return launch_status();
+  GPRTO_CUDA(cudaMemcpyAsync(h->small_pin + o_nll, h->small_dev + o_nll, size_t(k) * 12, cudaMemcpyDeviceToHost, s));
+  GPRTO_CUDA(cudaStreamSynchronize(s));
+  memcpy(nll_host, h->small_pin + o_nll, size_t(k) * 8);
+  memcpy(status_host, h->small_pin + o_st, size_t(k) * 4);
+  return 0;
 }
 
 int gprto_argmin(gprto_t* h, int64_t B, int64_t S, const double* val, double* best_val, int64_t* best_idx, void* stream) {

@@ -83,7 +83,8 @@ __device__ __forceinline__ void ch_cholesky(double* A, int n, int ld, int* s_inf
 __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, int d, const double* __restrict__ Xn,
                                                                   const double* __restrict__ Yn,
                                                                   const double* __restrict__ theta_all, double jitter,
-                                                                  double* __restrict__ nll, int32_t* __restrict__ status) {
+                                                                  double* __restrict__ nll, int32_t* __restrict__ status,
+                                                                  const int32_t* __restrict__ gidx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ld = ch_ld(n);
   double* A = reinterpret_cast<double*>(smem_raw);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   __shared__ int s_info;
   __shared__ double s_logdet;
   const int64_t bs = blockIdx.x;
-  const int64_t b = bs / S;
+  const int64_t b = gidx ? gidx[bs] : bs / S;
   const double* theta = theta_all + bs * (d + 2);
   ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = Yn[b * n + i];

@@ -162,7 +162,7 @@ template <int NT, int DT>
 __global__ void __launch_bounds__(16 * NT, 2)
 k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const double* __restrict__ Yn,
                   const double* __restrict__ theta_all, double jitter, double* __restrict__ nll,
-                  int32_t* __restrict__ status) {
+                  int32_t* __restrict__ status, const int32_t* __restrict__ gidx) {
   using C = K3LA<NT>;
   constexpr int UW = C::UW, TILES = C::TILES, SLOTS = C::SLOTS, NP = C::NP, LDP = K3R_LDP, THREADS = C::THREADS;
   constexpr int UTHREADS = 32 * UW;
@@ -184,7 +184,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int64_t bs = blockIdx.x;
-  const int64_t b = bs / S;
+  const int64_t b = gidx ? gidx[bs] : bs / S;      // gidx: problem -> data set indirection (indexed entry point)
   const double* theta = theta_all + bs * (d + 2);
 
   for (int e = tid; e < NP * d; e += THREADS) Xs[e] = (e / d) < n ? Xn[b * int64_t(n) * d + e] : 0.0;
@@ -384,7 +384,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
 
 template <int NT, int DT>
 int launch_k3la_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
-                  double* nll, int32_t* status, cudaStream_t s) {
+                  double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   const size_t smem = k3la_smem_bytes<NT>(d);
   static bool configured = false;
   if (!configured) {
@@ -396,33 +396,33 @@ int launch_k3la_d(int64_t B, int S, int n, int d, const double* Xn, const double
     cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k3_nlml_la_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status);
+  k3_nlml_la_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
 template <int NT>
 int launch_k3la(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
-                double* nll, int32_t* status, cudaStream_t s) {
+                double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   switch (d) {
-    case 2: return launch_k3la_d<NT, 2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 3: return launch_k3la_d<NT, 3>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+    case 2: return launch_k3la_d<NT, 2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 3: return launch_k3la_d<NT, 3>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
   }
-  return launch_k3la_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+  return launch_k3la_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
 // Look-ahead kernel where it measured faster than k3_nlml_tile_kernel (B200, d = 3: n = 64: 3.21e7 vs 3.08e7 evals/s,
 // n = 80: 1.81e7 vs 2.06e7 (so not used), n = 96: 1.35e7 vs 1.07e7, n = 112: 1.06e7 vs 7.4e6, n = 128: 8.4e6 vs 5.9e6);
 // returns GPRTO_EUNSUPPORTED otherwise (the caller falls back to launch_nlml_reg).
 inline int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta,
-                          double jitter, double* nll, int32_t* status, cudaStream_t s) {
+                          double jitter, double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   if (n > K3R_MAXN || d > K3R_MAXD || n <= 48) return GPRTO_EUNSUPPORTED;
   const int nt = (n + 15) / 16 * 2;
   switch (nt) {
-    case 8: return launch_k3la<8>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 12: return launch_k3la<12>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 14: return launch_k3la<14>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 16: return launch_k3la<16>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+    case 8: return launch_k3la<8>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 12: return launch_k3la<12>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 14: return launch_k3la<14>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 16: return launch_k3la<16>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
   }
   return GPRTO_EUNSUPPORTED;
 }

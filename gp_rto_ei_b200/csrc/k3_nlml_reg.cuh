@@ -36,7 +36,8 @@ template <int NT, int DT>
 __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k3_nlml_tile_kernel(int S, int n, int d_rt, const double* __restrict__ Xn,
                                                                const double* __restrict__ Yn,
                                                                const double* __restrict__ theta_all, double jitter,
-                                                               double* __restrict__ nll, int32_t* __restrict__ status) {
+                                                               double* __restrict__ nll, int32_t* __restrict__ status,
+                                                               const int32_t* __restrict__ gidx) {
   constexpr int W = NT / 2, NP = 8 * NT, SLOTS = NT + 1, LDP = K3R_LDP, THREADS = 32 * W;
   const int d = DT > 0 ? DT : d_rt;      // DT > 0: compile-time input dimension (unrolled distance loops)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int64_t bs = blockIdx.x;
-  const int64_t b = bs / S;
+  const int64_t b = gidx ? gidx[bs] : bs / S;      // gidx: problem -> data set indirection (indexed entry point)
   const double* theta = theta_all + bs * (d + 2);
 
   for (int e = tid; e < NP * d; e += THREADS) Xs[e] = (e / d) < n ? Xn[b * int64_t(n) * d + e] : 0.0;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
 
 template <int NT, int DT>
 int launch_k3r_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
-                 double* nll, int32_t* status, cudaStream_t s) {
+                 double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   const size_t smem = k3r_smem_bytes<NT>(d);
   static bool configured = false;
   if (!configured) {
@@ -299,34 +300,34 @@ int launch_k3r_d(int64_t B, int S, int n, int d, const double* Xn, const double*
     cudaFuncSetAttribute(k3_nlml_tile_kernel<NT, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k3_nlml_tile_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status);
+  k3_nlml_tile_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
 template <int NT>
 int launch_k3r(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
-               double* nll, int32_t* status, cudaStream_t s) {
+               double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   switch (d) {   // the dimensions of the published problems get unrolled distance loops
-    case 2: return launch_k3r_d<NT, 2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 3: return launch_k3r_d<NT, 3>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+    case 2: return launch_k3r_d<NT, 2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 3: return launch_k3r_d<NT, 3>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
   }
-  return launch_k3r_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+  return launch_k3r_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
 inline int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta,
-                           double jitter, double* nll, int32_t* status, cudaStream_t s) {
+                           double jitter, double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   if (n > K3R_MAXN || d > K3R_MAXD) return GPRTO_EUNSUPPORTED;
   const int nt = (n + 15) / 16 * 2;       // even number of 8-row tiles
   switch (nt) {
-    case 2: return launch_k3r<2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 4: return launch_k3r<4>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 6: return launch_k3r<6>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 8: return launch_k3r<8>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 10: return launch_k3r<10>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 12: return launch_k3r<12>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 14: return launch_k3r<14>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
-    case 16: return launch_k3r<16>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s);
+    case 2: return launch_k3r<2>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 4: return launch_k3r<4>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 6: return launch_k3r<6>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 8: return launch_k3r<8>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 10: return launch_k3r<10>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 12: return launch_k3r<12>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 14: return launch_k3r<14>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    case 16: return launch_k3r<16>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
   }
   return GPRTO_EUNSUPPORTED;
 }

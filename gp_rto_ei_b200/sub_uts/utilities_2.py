@@ -64,14 +64,14 @@ def _fit_group(handle, Xn_dev, Yn_dev_rows, bounds_rows, multi_start):
             owner.append(g)
     owner = np.asarray(owner)
 
+    Xg = Xn_dev.unsqueeze(0).expand(G, n, d).contiguous()          # one copy of X per GP (they share it), device-resident
+
     def fun_batch(inst, P):
-        gsel = torch.as_tensor(owner[inst], device=handle.device)
-        Xb = Xn_dev.unsqueeze(0).expand(len(inst), n, d).contiguous()
-        Yb = Yn_dev_rows.index_select(0, gsel).contiguous()
-        nll, st = handle.nlml(Xb, Yb, _dev(P, handle).unsqueeze(1), jitter=_JITTER)
-        out = nll.reshape(-1).cpu().numpy()
-        if np.isnan(out).any():                                          # NaN <=> non-zero status: one D2H instead of two
-            handle.raise_on_failure(st, 'negative_loglikelihood')        # numpy.linalg.LinAlgError as utilities_2.py:107
+        # one synchronous C call per SLSQP round: theta + owner index up, NLML + status down (pinned arena in the handle)
+        out, st = handle.nlml_indexed_host(Xg, Yn_dev_rows, owner[inst], P, jitter=_JITTER)
+        if st.any():
+            first = int(np.flatnonzero(st)[0])                           # numpy.linalg.LinAlgError as utilities_2.py:107
+            raise np.linalg.LinAlgError('Matrix is not positive definite (negative_loglikelihood, problem %d of %d)' % (first, len(st)))
         return out
 
     res = slsqp_batch.minimize_batch(fun_batch, x0s, bnds, ftol=1e-12, maxiter=10000, inst_ids=list(range(len(x0s))))
@@ -402,17 +402,16 @@ class ITR_GP_RTO:
 
         def evaluate(P):
             Xq = P + xk.reshape(1, ndim)
-            cand = _dev(Xq, h)
-            prior = np.array([float(self.obj_model(x)) for x in Xq])
-            sc = h.posterior_acq(obj_gp, cand.unsqueeze(0), _dev(prior, h).unsqueeze(0), fb, self.obj, want=('score',))['score'][0]
+            prior = np.array([[float(self.obj_model(x)) for x in Xq]])
+            sc = h.posterior_acq_host_np(obj_gp, Xq[None], prior, fb, self.obj, want=('score',))['score'][0]
             cons = np.empty((P.shape[0], ng + 1))
             if ng:
                 cprior = np.array([[float(np.asarray(self.cons_model[g](x)).reshape(-1)[0]) for x in Xq] for g in range(ng)])
-                cm = h.posterior_acq(con_gp, cand.unsqueeze(0).expand(ng, -1, -1).contiguous(), _dev(cprior, h), None,
-                                     api.ACQ_MEAN, want=('score',))['score']
-                cons[:, :ng] = cm.T.cpu().numpy()
+                cm = h.posterior_acq_host_np(con_gp, np.broadcast_to(Xq, (ng,) + Xq.shape), cprior, None, api.ACQ_MEAN,
+                                             want=('score',))['score']
+                cons[:, :ng] = cm.T
             cons[:, ng] = self.Delta0 ** 2 - np.einsum('ij,ij->i', P, P)
-            return sc.cpu().numpy(), cons
+            return sc, cons
 
         def fun_batch(inst, P):
             f, c = evaluate(P)

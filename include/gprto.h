@@ -78,6 +78,14 @@ int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* X
 int gprto_nlml(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, const double* Yn,
                const double* theta, double jitter, double* nll, int32_t* status, void* stream);
 
+/* Synchronous small-batch form for host-driven optimisers (the lock-step SLSQP rounds of the drop-in class): k problems,
+ * problem i uses data set gp_index_host[i] of the G device-resident ones (Xn[G,n,d], Yn[G,n]) with the hyper-parameters
+ * theta_host[i,:]; theta, index and results travel through one pinned arena and one stream owned by the handle; returns
+ * after nll_host[k] / status_host[k] are filled.  Same kernels and results as gprto_nlml. */
+int gprto_nlml_indexed_host(gprto_t* h, int64_t G, int64_t k, int n, int d, const double* Xn, const double* Yn,
+                            const int32_t* gp_index_host, const double* theta_host, double jitter,
+                            double* nll_host, int32_t* status_host);
+
 /* Row-wise arg-min with numpy.argmin semantics (first minimum wins; a NaN wins over everything;
  * replaces utilities_2.py:166 and :991).  val[B,S] -> best_val[B], best_idx[B]. */
 int gprto_argmin(gprto_t* h, int64_t B, int64_t S, const double* val, double* best_val, int64_t* best_idx,
