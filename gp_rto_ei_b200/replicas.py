@@ -4,9 +4,11 @@ sharded over the GPUs of one box, gathered with one NCCL all-gather of (objectiv
 The reference runs its 30 "Monte-Carlo" episodes sequentially in one Python process sharing one RNG stream
 (run_simple/main_simple.py:174, run_WO/main_WO_prior_EI.py:105).  Here replica r is an independent unit seeded with
 ``np.random.seed(r); random.seed(r)`` (both RNGs: the reference leaves the stdlib one unseeded, utilities_2.py:684), so
-any replica can be reproduced on its own.  Rank k of K owns replicas [lo, hi) = parallel.shard_range(R, k, K); a rank may
-fan its shard out over several worker processes that share its GPU (the episode is host-bound: SciPy's SLSQP state
-machine runs in Python), each with its own library handle.  The only collective is the final gather.
+any replica can be reproduced on its own.  Rank k of K owns replicas [lo, hi) = parallel.shard_range(R, k, K) and runs
+them one after the other (an episode is host-bound - SciPy's SLSQP state machine runs in Python - at 0.87 s for the toy
+problem against ~26 s for the reference).  `--workers W` fans a rank's shard out over W processes sharing its GPU; without
+MPS the processes time-slice the device and this measured SLOWER (128 toy replicas on 4 GPUs: 49.6 s with 4 workers per
+GPU vs ~30 s expected with 1), so the default is 1.  The only collective is the final gather.
 
     python -m torch.distributed.run --nproc-per-node 8 -m gp_rto_ei_b200.replicas --replicas 8192 --problem wo --workers 4
     python -m gp_rto_ei_b200.replicas --replicas 16 --problem simple            (single GPU)
