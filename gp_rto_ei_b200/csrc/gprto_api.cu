@@ -10,9 +10,9 @@
 #include <cstring>
 #include <new>
 
+#define GPRTO_API_TU 1
+#include "gprto_launch.h"
 #include "k23_chol.cuh"
-#include "k3_nlml_reg.cuh"
-#include "k3_nlml_la.cuh"
 #include "k4_posterior.cuh"
 
 using namespace gprto;
@@ -82,52 +82,15 @@ int ensure_part(gprto_t* h, size_t count) {
   return 0;
 }
 
-template <int NB, int D>
-int launch_k4_dmma(gprto_t* h, const K4Params& p, cudaStream_t s) {
-  constexpr size_t smem = k4_smem_bytes<NB, D>();
-  static bool configured = false;   // attribute is per-function, idempotent
-  if (!configured) {
-    int rc = set_smem(k4_dmma_kernel<NB, D>, smem);
-    if (rc) return rc;
-    cudaFuncSetAttribute(k4_dmma_kernel<NB, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
-  dim3 grid((unsigned)p.B, p.nchunks);      // GP on x (2^31-1 limit), candidate chunk on y
-  k4_dmma_kernel<NB, D><<<grid, K4_THREADS, smem, s>>>(p);
-  h->launches++;
-  return launch_status();
-}
-
-template <int NB>
-int dispatch_k4_d(gprto_t* h, const K4Params& p, cudaStream_t s) {
-  switch (p.d) {
-    case 1: return launch_k4_dmma<NB, 1>(h, p, s);
-    case 2: return launch_k4_dmma<NB, 2>(h, p, s);
-    case 3: return launch_k4_dmma<NB, 3>(h, p, s);
-    case 4: return launch_k4_dmma<NB, 4>(h, p, s);
-    case 5: return launch_k4_dmma<NB, 5>(h, p, s);
-    case 6: return launch_k4_dmma<NB, 6>(h, p, s);
-    case 7: return launch_k4_dmma<NB, 7>(h, p, s);
-    case 8: return launch_k4_dmma<NB, 8>(h, p, s);
-  }
-  return GPRTO_EUNSUPPORTED;
-}
-
 int dispatch_k4(gprto_t* h, const K4Params& p, cudaStream_t s) {
   const int nb = (p.n + 7) / 8;
-  switch (nb) {
-    case 1: return dispatch_k4_d<1>(h, p, s);
-    case 2: return dispatch_k4_d<2>(h, p, s);
-    case 3: return dispatch_k4_d<3>(h, p, s);
-    case 4: return dispatch_k4_d<4>(h, p, s);
-    case 5: case 6: return dispatch_k4_d<6>(h, p, s);
-    case 7: case 8: return dispatch_k4_d<8>(h, p, s);
-    case 9: case 10: return dispatch_k4_d<10>(h, p, s);
-    case 11: case 12: return dispatch_k4_d<12>(h, p, s);
-    case 13: case 14: return dispatch_k4_d<14>(h, p, s);
-    case 15: case 16: return dispatch_k4_d<16>(h, p, s);
-  }
-  return GPRTO_EUNSUPPORTED;
+  int rc;
+  if (nb <= 4) rc = gprto_k4_launch_a(nb, p, s);
+  else if (nb <= 8) rc = gprto_k4_launch_b(nb, p, s);
+  else if (nb <= 12) rc = gprto_k4_launch_c(nb, p, s);
+  else rc = gprto_k4_launch_d(nb, p, s);
+  if (rc != GPRTO_EUNSUPPORTED) h->launches++;
+  return rc;
 }
 
 constexpr int K4_DMMA_MAXN = 128, K4_DMMA_MAXD = 8;

@@ -1,0 +1,3 @@
+// Translation unit holding every K3 register-resident kernel instance (see gprto_launch.h).
+#include "k3_nlml_reg.cuh"
+#include "k3_nlml_la.cuh"

@@ -12,6 +12,7 @@
 //                     bar.sync(Y) all; update warps: panel rows of column kb+1; bar.sync(Z) among update warps.
 //     z and the panel are double-buffered; the right-hand side update rides on the diagonal tiles as before.
 #pragma once
+#include "gprto_launch.h"
 #include "gprto_math.cuh"
 #include "k3_nlml_reg.cuh"
 #include <type_traits>
@@ -414,8 +415,8 @@ int launch_k3la(int64_t B, int S, int n, int d, const double* Xn, const double* 
 // Look-ahead kernel where it measured faster than k3_nlml_tile_kernel (B200, d = 3: n = 64: 3.21e7 vs 3.08e7 evals/s,
 // n = 80: 1.81e7 vs 2.06e7 (so not used), n = 96: 1.35e7 vs 1.07e7, n = 112: 1.06e7 vs 7.4e6, n = 128: 8.4e6 vs 5.9e6);
 // returns GPRTO_EUNSUPPORTED otherwise (the caller falls back to launch_nlml_reg).
-inline int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta,
-                          double jitter, double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
+int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
+                   double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
   if (n > K3R_MAXN || d > K3R_MAXD || n <= 48) return GPRTO_EUNSUPPORTED;
   const int nt = (n + 15) / 16 * 2;
   switch (nt) {

@@ -16,6 +16,7 @@
 //              The panel is double-buffered: 3 barriers per block step.
 //   K itself is never written to memory: each lane evaluates the SE-ARD entries of its own fragments.
 #pragma once
+#include "gprto_launch.h"
 #include "gprto_math.cuh"
 #ifdef K3_TIMING
 #include <cstdio>
@@ -23,8 +24,6 @@
 
 namespace gprto {
 
-constexpr int K3R_MAXN = 128;
-constexpr int K3R_MAXD = 8;
 constexpr int K3R_LDP = 12;
 
 template <int NT>
@@ -315,8 +314,8 @@ int launch_k3r(int64_t B, int S, int n, int d, const double* Xn, const double* Y
   return launch_k3r_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
-inline int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta,
-                           double jitter, double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
+int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
+                    double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
   if (n > K3R_MAXN || d > K3R_MAXD) return GPRTO_EUNSUPPORTED;
   const int nt = (n + 15) / 16 * 2;       // even number of 8-row tiles
   switch (nt) {

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
   }
 }
 
+#ifdef GPRTO_API_TU      // non-template kernels: defined in the API translation unit only
 // Generic path: any n <= K4G_MAXN, any d <= K4G_MAXD; one thread per candidate, k* in local memory,
 // full (non-symmetrised) quadratic form exactly as the reference writes it (:267-268).  Used outside the
 // DMMA path's limits and as an independent cross-check of it in the tests.
@@ -299,6 +300,8 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
   }
 }
 
+#endif  // GPRTO_API_TU
+
 // Materialise the sampler's candidates (same function as K4's fused mode): cand[b, c, :] = centre[b] + radius[b] * u.
 // With idx != nullptr only candidate idx[b] of each GP is produced (out[b, :]) - the coordinates of the per-GP best.
 template <int D>
@@ -315,6 +318,7 @@ __global__ void sample_candidates_kernel(int64_t B, int64_t m, const double* __r
   for (int dd = 0; dd < D; ++dd) out[e * D + dd] = fma(radius[b], u[dd], centre[b * D + dd]);
 }
 
+#ifdef GPRTO_API_TU
 // Row-wise arg-min (numpy.argmin semantics) - also the second pass of K4's per-GP best and the
 // multistart selection of utilities_2.py:166.  One warp per row.
 __global__ void argmin_rows_kernel(int64_t B, int64_t S, const double* __restrict__ val,
@@ -338,5 +342,7 @@ __global__ void argmin_rows_kernel(int64_t B, int64_t S, const double* __restric
   }
   if (lane == 0) { best_val[row] = bv; best_idx[row] = bi; }
 }
+
+#endif  // GPRTO_API_TU
 
 }  // namespace gprto
