@@ -240,7 +240,9 @@ int gprto_limits(int64_t limits[4]) {
   if (!limits) return GPRTO_EINVAL;
   limits[0] = K4_DMMA_MAXN;
   limits[1] = K3R_MAXN;
-  limits[2] = K4G_MAXN;
+  int nmax = 1;
+  while (ch_smem_bytes(nmax + 1, CH_MAXD) <= 227 * 1024) ++nmax;      // factor / generic NLML keep the matrix in shared memory
+  limits[2] = nmax;
   limits[3] = CH_MAXD;
   return 0;
 }

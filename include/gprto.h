@@ -50,7 +50,8 @@ int  gprto_destroy(gprto_t* h);
 const char* gprto_version(void);
 const char* gprto_error_string(int code);
 /* limits[0] = max n of the DMMA posterior path, [1] = max n of the register-resident NLML path,
- * [2] = max n overall, [3] = max d. */
+ * [2] = max n of gprto_factor / gprto_nlml (matrix in shared memory; the generic posterior path alone goes to n = 512),
+ * [3] = max d. */
 int  gprto_limits(int64_t limits[4]);
 int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead;
                                                                          "cov_kernel": kernel of gprto_cov_se_ard only: 0 SE-ARD, 1 Matern-3/2, 2 Matern-5/2 */
