@@ -242,6 +242,16 @@ def _check_nlml(handle, dev, X, y, thetas, ref, fail, label):
 def test_k3_nlml_cfg4_golden(handle, dev):
     g = load_golden('cfg4_small.npz')
     _check_nlml(handle, dev, g['X'], g['y'], g['theta'], g['nlml'], g['fail'], 'cfg4 n=128')
+    # multistart selection (utilities_2.py:166): identical start index wherever the gap to the runner-up exceeds 1e-9
+    nz = handle.normalise(T(g['X'], dev), T(g['y'], dev))
+    nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(g['theta'], dev))
+    bv, bi = handle.argmin(nll)
+    for b in range(g['X'].shape[0]):
+        ref = g['nlml'][b]
+        order = np.sort(ref)
+        if order[1] - order[0] > 1e-9 * abs(order[0]):
+            assert int(bi[b]) == int(np.argmin(ref))
+        assert float(bv[b]) == float(nll[b, int(bi[b])])
 
 
 def test_k3_nlml_small_and_ragged(handle, dev):
