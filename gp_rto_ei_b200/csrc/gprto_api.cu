@@ -32,8 +32,6 @@ struct gprto_handle {
   // host-path staging
   cudaStream_t st[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-  double* pin_in[2] = {nullptr, nullptr};
-  double* pin_out[2] = {nullptr, nullptr};
   double* dev_in[2] = {nullptr, nullptr};
   double* dev_out[2] = {nullptr, nullptr};
   size_t stage_in_cap = 0, stage_out_cap = 0;
@@ -277,8 +275,6 @@ int gprto_destroy(gprto_t* h) {
   if (h->small_stream) cudaStreamDestroy(h->small_stream);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
-    if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
-    if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
     if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);

@@ -30,13 +30,8 @@ namespace gprto {
 template <int NT>
 struct K3LA {
   static constexpr int W = NT / 2;                 // warps per CTA (1 panel + update warps [+ 1 idle])
-#ifdef K3LA_ISOLATE
-  // the warp sharing the panel warp's scheduler (warp ids are dealt round-robin to the 4 schedulers) stays idle, so
-  // the pivot chain's FP64 instructions do not queue behind that warp's DMMAs
-  static constexpr int IDLE = (W >= 8) ? 1 : 0;
-#else
+  // (idling the warp that shares the panel warp's scheduler was measured slower: 7.5e6 vs 8.3e6 evals/s at n = 128)
   static constexpr int IDLE = 0;
-#endif
   static constexpr int UW = W - 1 - IDLE;
   static constexpr int TILES = NT * (NT + 1) / 2;
   static constexpr int SLOTS = (TILES + UW - 1) / UW;

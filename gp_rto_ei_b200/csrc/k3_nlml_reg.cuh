@@ -217,42 +217,6 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
       aA[s] = buf[(8 * rowA + g) * LDP + 4 * s + t];
       aB[s] = buf[(8 * rowB + g) * LDP + 4 * s + t];
     }
-#ifdef K3_BRANCHFREE_UPDATE
-    // (measured slower: 4.7e6 vs 6.1e6 evals/s at n=128 - the extra DMMAs of the co-resident CTA delay the FP64
-    // instructions on the pivot chain, which share the pipe)  Branch-free: every slot issues its two DMMAs each step; finished tiles (J <= kb) get a zero B operand, which
-    // leaves their (already spilled, never read again) accumulators unchanged.  Twice the DMMA count at the end of the
-    // factorisation, but no BSSY/BSYNC per tile, so the scheduler can hoist all fragment loads ahead of the MMAs -
-    // this phase is latency-bound (2 warps per scheduler), not pipe-bound.
-    double bq0[SLOTS], bq1[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int J = (s <= w) ? s : s - w - 1;
-      const double l0 = buf[(8 * J + g) * LDP + t], l1 = buf[(8 * J + g) * LDP + 4 + t];
-      bq0[s] = J > kb ? -l0 : 0.0;
-      bq1[s] = J > kb ? -l1 : 0.0;
-    }
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) dmma884(C0[s], C1[s], (s <= w) ? aA[0] : aB[0], bq0[s]);
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) dmma884(C0[s], C1[s], (s <= w) ? aA[1] : aB[1], bq1[s]);
-    {
-      // y'_J -= L(J,kb) z_kb on the warp holding diagonal tile (J,J): slot w (row A) and slot NT (row B)
-      const int Jb = rowB;                       // slot NT: (rowB, rowB)
-      double pb = fma(bq0[NT], zs[t], bq1[NT] * zs[4 + t]);
-      double pa = 0.0;
-#pragma unroll
-      for (int s = 0; s < SLOTS - 1; ++s)
-        if (s == w) pa = fma(bq0[s], zs[t], bq1[s] * zs[4 + t]);   // slot w: (rowA, rowA); zero operand once finished
-      pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-      pb += __shfl_xor_sync(0xffffffffu, pb, 1);
-      pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-      pb += __shfl_xor_sync(0xffffffffu, pb, 2);
-      if (t == 0) {
-        if (rowA > kb) ys[8 * rowA + g] += pa;
-        if (Jb > kb) ys[8 * Jb + g] += pb;
-      }
-    }
-#else
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const int J = (s <= w) ? s : s - w - 1;
@@ -270,7 +234,6 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
         }
       }
     }
-#endif
     K3_MARK(4)
   }
 #ifdef K3_TIMING

@@ -471,3 +471,25 @@ def test_posterior_mean_is_linear_in_the_observations(handle, dev):
     scale = float(res[0]['mean'].abs().max() + res[1]['mean'].abs().max())
     assert float((res[2]['mean'] - lin).abs().max()) < 1e-9 * scale
     assert torch.equal(res[0]['var'], res[1]['var']) and torch.equal(res[0]['var'], res[2]['var'])
+
+
+def test_pack_best_records_roundtrip(handle, dev):
+    """K5 send buffer: 16-byte (score, index + offset) records, bit-exact through gp_rto_ei_b200.parallel."""
+    from gp_rto_ei_b200 import parallel
+    score = torch.tensor([1.5, -2.0, float('inf'), 0.0], dtype=torch.float64, device=dev)
+    idx = torch.tensor([0, 4095, 17, 2 ** 40], dtype=torch.int64, device=dev)
+    rec = handle.pack_best(score, idx, idx_offset=1000)
+    s2, i2 = parallel.unpack_records(rec)
+    assert torch.equal(s2, score) and torch.equal(i2, idx + 1000)
+    assert parallel.allgather_records(rec) is rec                     # single process: no collective
+    assert parallel.global_argmin(rec)[:2] == (-2.0, 5095)
+
+
+def test_host_entry_with_prior_and_lcb(handle, dev):
+    w = workloads.cfg3_torch(dev, seed=10, B=7, n=24, d=2, m=333)
+    gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
+    prior = torch.randn(7, 333, dtype=torch.float64, device=dev)
+    ref = handle.posterior_acq(gd, w['cand'], prior, None, 2)
+    out = handle.posterior_acq_host_np(gd, w['cand'].cpu().numpy(), prior.cpu().numpy(), None, 2, want=('mean', 'var', 'score', 'best'))
+    for k in ('mean', 'var', 'score', 'best_score', 'best_idx'):
+        assert np.array_equal(out[k], ref[k].cpu().numpy()), k
