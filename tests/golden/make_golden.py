@@ -15,6 +15,7 @@ Files written
                     (nan + flag where the reference raises LinAlgError).
   rto_simple.npz    three short seeded episodes of the reference's ITR_GP_RTO on the toy problem (trajectories, TR radii,
                     backtrack flags).
+  rto_wo.npz        the same for the Williams-Otto configuration (2 constraint GPs, ellipse start sampling, model prior).
   ragged.npz        edge cases: n=1, n=2, n=7 (not a multiple of 8), d=1 and d=5, zero variance (candidate on a
                     noise-free data point), far-tail EI.
 """
@@ -251,6 +252,52 @@ def rto_simple():
     np.savez_compressed(os.path.join(HERE, 'rto_simple.npz'), **out)
 
 
+def rto_wo():
+    """Short seeded episodes of the reference's ITR_GP_RTO in the Williams-Otto configuration of
+    run_WO/main_WO_prior_EI.py (ng = 2 constraint GPs, scale_inputs=True -> Ellipse_sampling, model prior, known noise).
+    casadi is not available, so the plant / model callables are this repo's NumPy Newton restatement
+    (gp_rto_ei_b200/sub_uts/systems.py) - the class under test is the reference's own driver and GP."""
+    import contextlib
+    import io
+    import random
+    from gp_rto_ei_b200.sub_uts import systems as S
+    out = {}
+    for tag, acq, noisy in (('wo_ei_noiseless', 3, False), ('wo_ei_noisy', 3, True), ('wo_mean_noisy', 1, True)):
+        def episode():
+            np.random.seed(0); random.seed(0)
+            model, plant = S.WO_model(), S.WO_system()
+            obj_sys = plant.WO_obj_sys_ca if noisy else plant.WO_obj_sys_ca_noise_less
+            cons_sys = [plant.WO_con1_sys_ca, plant.WO_con2_sys_ca] if noisy else [plant.WO_con1_sys_ca_noise_less, plant.WO_con2_sys_ca_noise_less]
+            Xtrain = np.array([[5.7, 74.], [6.35, 74.9], [6.6, 75.], [6.75, 79.]])
+            with contextlib.redirect_stdout(io.StringIO()):
+                rto = ref.ITR_GP_RTO(model.WO_obj_ca, obj_sys, [model.WO_con1_model_ca, model.WO_con2_model_ca], cons_sys,
+                                     np.array([6.9, 83.]), 0.25, 0.7, 0.2, 0.8, 0.8, 1.2, 3, ['data0', Xtrain], np.array([[4., 7.], [70., 100.]]),
+                                     obj_setting=acq, noise=[0.5 ** 2, 5e-8, 5e-8], multi_opt=5, multi_hyper=3, TR_scaling=False,
+                                     TR_curvature=False, store_data=True, inner_TR=False, scale_inputs=True)
+                return rto.RTO_routine()
+        X_opt, y_opt, TR_l, xnew, backtrack = episode()
+        nll0, inf0 = ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np
+        ulp = 1.0 + 2.0 ** -52
+
+        def nll1(self, hyper, X, Y):
+            return nll0(self, hyper, X, Y) * ulp
+
+        def inf1(self, x):
+            r = inf0(self, x)
+            return (r[0] * ulp, r[1] * ulp) if isinstance(r, tuple) else r * ulp
+        ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np = nll1, inf1
+        try:
+            Xp, _, TRp, _, btp = episode()
+        finally:
+            ref.GP_model.negative_loglikelihood, ref.GP_model.GP_inference_np = nll0, inf0
+        out.update({tag + '_X_opt': X_opt, tag + '_y_opt': y_opt, tag + '_TR_l': np.array(TR_l, dtype=float),
+                    tag + '_backtrack': np.array(backtrack, dtype=bool), tag + '_X_opt_ulp': Xp,
+                    tag + '_same_signature_ulp': np.array(np.array_equal(TRp, TR_l) and list(btp) == list(backtrack))})
+        print('rto', tag, 'TR', TR_l, 'backtrack', backtrack, 'x', np.asarray(xnew).ravel(),
+              '| one-ulp self-sensitivity max|dX| = %.3e, same TR/backtrack: %s' % (np.abs(Xp - X_opt).max(), out[tag + '_same_signature_ulp']))
+    np.savez_compressed(os.path.join(HERE, 'rto_wo.npz'), **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         globals()[sys.argv[1]]()
@@ -260,4 +307,5 @@ if __name__ == '__main__':
     cfg4_small()
     ragged()
     rto_simple()
+    rto_wo()
     print('golden vectors written to', HERE)

@@ -146,3 +146,30 @@ def test_replica_driver_is_reproducible_per_seed(u2):
     assert a == b and set(a) >= {'objective', 'feasible', 'x', 'seed'}
     w = replicas.run_replica(0, problem='wo', obj_setting=3, n_iter=2, multi_opt=4, multi_hyper=3)
     assert 4.0 <= w['x'][0] <= 7.0 and 70.0 <= w['x'][1] <= 100.0 and -200 < w['objective'] < 200   # -profit; the optimum is -75.8
+
+
+@pytest.mark.parametrize('tag,acq,noisy', [('wo_ei_noiseless', 3, False), ('wo_ei_noisy', 3, True), ('wo_mean_noisy', 1, True)])
+def test_rto_episode_williams_otto_configuration(u2, tag, acq, noisy):
+    """Config 2 (run_WO/main_WO_prior_EI.py): 1 + 2 GPs per iteration, scale_inputs=True (ellipse start sampling), model
+    prior, known noise.  Golden = the reference's own ITR_GP_RTO / GP_model driven with the same NumPy plant callables.
+    Same criterion as the toy problem: identical trust-region / backtrack signature, iterates within 100x the reference's
+    one-ulp self-sensitivity (floor 1e-5 in inputs that span [4,7] x [70,100])."""
+    from gp_rto_ei_b200.sub_uts import systems as S
+    g = load_golden('rto_wo.npz')
+    np.random.seed(0); random.seed(0)
+    model, plant = S.WO_model(), S.WO_system()
+    obj_sys = plant.WO_obj_sys_ca if noisy else plant.WO_obj_sys_ca_noise_less
+    cons_sys = [plant.WO_con1_sys_ca, plant.WO_con2_sys_ca] if noisy else [plant.WO_con1_sys_ca_noise_less, plant.WO_con2_sys_ca_noise_less]
+    Xtrain = np.array([[5.7, 74.], [6.35, 74.9], [6.6, 75.], [6.75, 79.]])
+    with contextlib.redirect_stdout(io.StringIO()):
+        rto = u2.ITR_GP_RTO(model.WO_obj_ca, obj_sys, [model.WO_con1_model_ca, model.WO_con2_model_ca], cons_sys, np.array([6.9, 83.]), 0.25,
+                            0.7, 0.2, 0.8, 0.8, 1.2, 3, ['data0', Xtrain], np.array([[4., 7.], [70., 100.]]), obj_setting=acq,
+                            noise=[0.5 ** 2, 5e-8, 5e-8], multi_opt=5, multi_hyper=3, TR_scaling=False, TR_curvature=False, store_data=True,
+                            inner_TR=False, scale_inputs=True)
+        X_opt, y_opt, TR_l, xnew, backtrack = rto.RTO_routine()
+    sens = np.abs(g[tag + '_X_opt_ulp'] - g[tag + '_X_opt']).max()
+    err = np.abs(X_opt - g[tag + '_X_opt']).max()
+    print('\n[rto %s] max |dX| vs reference: %.3e (reference one-ulp self-sensitivity %.3e)' % (tag, err, sens))
+    assert np.allclose(np.array(TR_l, dtype=float), g[tag + '_TR_l'], rtol=0, atol=1e-15)
+    assert list(backtrack) == list(g[tag + '_backtrack'])
+    assert err < max(100 * sens, 1e-5)
