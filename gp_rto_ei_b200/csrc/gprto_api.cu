@@ -50,6 +50,8 @@ namespace {
     if (e_ != cudaSuccess) return -static_cast<int>(e_);   \
   } while (0)
 
+constexpr int64_t kMaxGridX = 2147483647LL;      // one CTA per problem: gridDim.x limit
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -104,6 +106,7 @@ int posterior_device(gprto_t* h, int64_t B, int n, int d, int64_t m, const doubl
   if (h->k4_path == GPRTO_K4_GENERIC) use_dmma = false;
   if (h->k4_path == GPRTO_K4_DMMA && !dmma_ok) return GPRTO_EUNSUPPORTED;
   if (!use_dmma && (n > K4G_MAXN || d > K4G_MAXD)) return GPRTO_EUNSUPPORTED;
+  if (B > kMaxGridX) return GPRTO_EUNSUPPORTED;
   if (!cand && !use_dmma) return GPRTO_EUNSUPPORTED;      // fused sampling lives in the DMMA kernel only
   K4Params p{};
   p.B = B; p.m = m; p.n = n; p.d = d; p.acq = acq;
@@ -201,6 +204,7 @@ int dispatch_sample(gprto_t* h, int64_t B, int d, int64_t m, const double* centr
 
 int nlml_device(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                 double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
+  if (B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
     int rc = GPRTO_EUNSUPPORTED;
     if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead kernel
@@ -307,7 +311,7 @@ int gprto_normalise(gprto_t* h, int64_t B, int n, int d, const double* X, const 
 int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, const double* theta, int add_noise,
                      double jitter, double* K, void* stream) {
   if (!h || B <= 0 || S <= 0 || n <= 0 || d <= 0 || !Xn || !theta || !K) return GPRTO_EINVAL;
-  if (d > CH_MAXD || size_t(n) * d * sizeof(double) > 200 * 1024) return GPRTO_EUNSUPPORTED;
+  if (d > CH_MAXD || size_t(n) * d * sizeof(double) > 200 * 1024 || B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
   const size_t smem = (size_t(n) * d + CH_MAXD) * sizeof(double);
   int rc = set_smem(cov_kernel, smem);
