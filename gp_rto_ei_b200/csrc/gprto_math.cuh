@@ -38,33 +38,6 @@ __device__ __forceinline__ double exp_fast(double a) {
   return a < -700.0 ? 0.0 : res;
 }
 
-// Table variant for warp-synchronous callers: lane l holds tv = 2^(l/32); exp(a) = 2^e * 2^(j/32) * exp(r) with
-// a = (32 e + j) ln2/32 + r, |r| <= ln2/64, degree-6 polynomial (4.4e-19 in exact arithmetic) and the table entry fetched
-// with a warp shuffle: 11 FP64-pipe instructions instead of 15.  Must be called by all 32 lanes.
-__device__ __forceinline__ double exp_fast_tab(double a, double tv) {
-  const double K32 = 46.16624130844683;               // 32 / ln2
-  const double L_HI = 0.021660849335603416;           // ln2 / 32, low 24 bits zero
-  const double L_LO = 5.689487495325457e-11;
-  const double MAGIC = 6755399441055744.0;
-  double t = fma(a, K32, MAGIC);
-  const int n = __double2loint(t);
-  const double nf = t - MAGIC;
-  double r = fma(nf, -L_HI, a);
-  r = fma(nf, -L_LO, r);
-  const double T = __shfl_sync(0xffffffffu, tv, n & 31);
-  double p = 0.001388893990147763;
-  p = fma(p, r, 0.008333374143420981);
-  p = fma(p, r, 0.04166666666636688);
-  p = fma(p, r, 0.1666666666642684);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  p *= T;
-  const int hi = __double2hiint(p) + (int)((unsigned)(n >> 5) << 20);
-  const double res = __hiloint2double(hi, __double2loint(p));
-  return a < -700.0 ? 0.0 : res;
-}
-
 // numpy.argmin ordering on (value, index): a NaN beats any number, ties go to the lower index.
 __device__ __forceinline__ bool better(double va, int64_t ia, double vb, int64_t ib) {
   const bool na = va != va, nb = vb != vb;

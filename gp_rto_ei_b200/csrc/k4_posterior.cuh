@@ -119,9 +119,6 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
   const double* At = As + 2 * t;
   const double* Mlane = Mf + lane;
 
-#ifdef K4_EXP_TABLE
-  const double exp_tv = exp2(double(lane) * (1.0 / 32.0));      // lane l: 2^(l/32)
-#endif
   double best_v = CUDART_INF;
   int64_t best_i = INT64_MAX;
 
@@ -158,11 +155,7 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
           const double df = x[dd] - Xt[(8 * (s >> 1) + (s & 1)) * D + dd];
           acc = fma(df * df, nhw[dd], acc);
         }
-#ifdef K4_EXP_TABLE
-        kv[s] = exp_fast_tab(acc, exp_tv);
-#else
         kv[s] = exp_fast(acc);
-#endif
       }
       double C0[NB], C1[NB];
 #pragma unroll
