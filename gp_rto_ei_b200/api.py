@@ -238,6 +238,8 @@ _default = {}
 
 
 def default_handle(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError('gp_rto_ei_b200 needs a CUDA device (sm_100); there is no CPU fallback')
     idx = torch.cuda.current_device() if device is None else device
     if idx not in _default:
         _default[idx] = Handle(idx)
