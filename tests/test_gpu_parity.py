@@ -493,3 +493,32 @@ def test_host_entry_with_prior_and_lcb(handle, dev):
     out = handle.posterior_acq_host_np(gd, w['cand'].cpu().numpy(), prior.cpu().numpy(), None, 2, want=('mean', 'var', 'score', 'best'))
     for k in ('mean', 'var', 'score', 'best_score', 'best_idx'):
         assert np.array_equal(out[k], ref[k].cpu().numpy()), k
+
+
+def test_full_size_cfg3_and_cfg4_properties(handle, dev):
+    """BASELINE.json's full sizes through size-independent properties.
+    cfg 3 (65,536 GPs x 4,096 candidates, n=64, d=3): variances non-negative, per-GP arg-min consistent with the score
+    array, and a slice of the batch recomputed on its own is bit-identical (no cross-GP coupling at any grid size).
+    cfg 4 (16,384 GPs x 64 Sobol starts, n=128): every factorisation succeeds, and the first GPs recomputed as a small
+    batch give bit-identical NLML values and the same selected start."""
+    w = workloads.cfg3_torch(dev, seed=0, B=65536, n=64, d=3, m=4096)
+    gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
+    assert int(gd['status'].abs().sum()) == 0
+    out = handle.posterior_acq(gd, w['cand'], None, w['f_best'], 3, want=('var', 'score', 'best'))
+    assert bool((out['var'] >= 0).all()) and bool(torch.isfinite(out['score']).all())
+    assert torch.equal(out['best_idx'], out['score'].argmin(dim=1))
+    sl = slice(40000, 40016)
+    sub = {k: v[sl].contiguous() for k, v in gd.items()}
+    out2 = handle.posterior_acq(sub, w['cand'][sl].contiguous(), None, w['f_best'][sl].contiguous(), 3, want=('var', 'score', 'best'))
+    assert torch.equal(out2['score'], out['score'][sl]) and torch.equal(out2['var'], out['var'][sl])
+    assert torch.equal(out2['best_idx'], out['best_idx'][sl])
+    del w, gd, out, out2
+    torch.cuda.empty_cache()
+    w = workloads.cfg4_torch(dev, seed=1, B=16384, n=128, d=3, S=64)
+    nz = handle.normalise(w['X'], w['y'])
+    nll, st = handle.nlml(nz['Xn'], nz['Yn'], w['theta'])
+    assert int((st != 0).sum()) == 0 and bool(torch.isfinite(nll).all())
+    bv, bi = handle.argmin(nll)
+    nll2, st2 = handle.nlml(nz['Xn'][:16].contiguous(), nz['Yn'][:16].contiguous(), w['theta'][:16].contiguous())
+    assert torch.equal(nll2, nll[:16])
+    assert torch.equal(handle.argmin(nll2)[1], bi[:16]) and torch.equal(bi, nll.argmin(dim=1))
