@@ -313,10 +313,16 @@ int gprto_cov_se_ard(gprto_t* h, int64_t B, int S, int n, int d, const double* X
   if (!h || B <= 0 || S <= 0 || n <= 0 || d <= 0 || !Xn || !theta || !K) return GPRTO_EINVAL;
   if (d > CH_MAXD || size_t(n) * d * sizeof(double) > 200 * 1024 || B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
-  const size_t smem = (size_t(n) * d + CH_MAXD) * sizeof(double);
-  int rc = set_smem(cov_kernel, smem);
+  const bool tiled = cov_smem_bytes(n, d, true) <= 48 * 1024;      // n <= ~76: at least 4 CTAs per SM keep their tile
+  const size_t smem = cov_smem_bytes(n, d, tiled);
+  int rc = tiled ? set_smem(cov_kernel<true>, smem) : set_smem(cov_kernel<false>, smem);
   if (rc) return rc;
-  cov_kernel<<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, h->cov_kernel_kind, K);
+  if (tiled) {
+    cudaFuncSetAttribute(cov_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cov_kernel<true><<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, h->cov_kernel_kind, K);
+  } else {
+    cov_kernel<false><<<(unsigned)(B * S), CH_THREADS, smem, (cudaStream_t)stream>>>(S, n, d, Xn, theta, add_noise, jitter, h->cov_kernel_kind, K);
+  }
   h->launches++;
   return launch_status();
 }

@@ -126,15 +126,36 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   }
 }
 
-// K1: Gram matrix to global memory (API parity with Cov_mat; the fused kernels never materialise K).
-// kind 0: SE-ARD (RBF branch, utilities_2.py:57-59); 1: Matern-3/2 (:61-63); 2: Matern-5/2 (:64-66), with
-// dist = sum (x - x')^2 / W and r = sqrt(dist) exactly as the reference forms them from cdist.
+// K1: Gram matrix to global memory (API parity with Cov_mat; the fused kernels never materialise K).  The only
+// HBM-bound kernel of the path: n^2 x 8 B written per matrix.  Each entry of the lower triangle is evaluated once
+// (half the exponentials), mirrored through a shared-memory tile, and the matrix leaves in fully coalesced 16-byte
+// stores.  kind 0: SE-ARD (RBF branch, utilities_2.py:57-59); 1: Matern-3/2 (:61-63); 2: Matern-5/2 (:64-66), with
+// dist = sum (x - x')^2 / W and r = sqrt(dist) as the reference forms them from cdist.
+__device__ __forceinline__ double cov_entry(const double* Xs, const double* nhw, int d, int i, int j, double c0, double sf2,
+                                            int kind) {
+  double acc = 0.0;                           // -dist / 2
+  for (int dd = 0; dd < d; ++dd) {
+    const double df = Xs[i * d + dd] - Xs[j * d + dd];
+    acc = fma(df * df, nhw[dd], acc);
+  }
+  if (kind == 0) return exp_fast(c0 + acc);
+  const double dist = -2.0 * acc, r = sqrt(dist);
+  if (kind == 1) return sf2 * (1.0 + 1.7320508075688772 * r) * exp(-1.7320508075688772 * r);
+  return sf2 * (1.0 + 2.23606797749979 * r + (5.0 / 3.0) * dist) * exp(-2.23606797749979 * r);
+}
+
+inline size_t cov_smem_bytes(int n, int d, bool tiled) {
+  return sizeof(double) * (size_t(n) * d + CH_MAXD + (tiled ? size_t(n) * (n | 1) : 0));
+}
+
+template <bool TILED>
 __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, const double* __restrict__ Xn,
                                                          const double* __restrict__ theta_all, int add_noise,
                                                          double jitter, int kind, double* __restrict__ K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Xs = reinterpret_cast<double*>(smem_raw);
   double* nhw = Xs + n * d;
+  double* tile = nhw + CH_MAXD;               // [n][n] when TILED
   const int64_t bs = blockIdx.x;
   const int64_t b = bs / S;
   const double* theta = theta_all + bs * (d + 2);
@@ -144,24 +165,30 @@ __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, co
   const double c0 = 2.0 * theta[d];
   const double sf2 = exp(c0);
   double* Kout = K + bs * int64_t(n) * n;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    const int lo = min(i, j), hi = max(i, j);   // evaluate (hi, lo) so the matrix is exactly symmetric
-    double acc = 0.0;                           // -dist / 2
-    for (int dd = 0; dd < d; ++dd) {
-      const double df = Xs[hi * d + dd] - Xs[lo * d + dd];
-      acc = fma(df * df, nhw[dd], acc);
-    }
-    double v;
-    if (kind == 0) {
-      v = exp_fast(c0 + acc);
-    } else {
-      const double dist = -2.0 * acc, r = sqrt(dist);
-      if (kind == 1) v = sf2 * (1.0 + 1.7320508075688772 * r) * exp(-1.7320508075688772 * r);
-      else v = sf2 * (1.0 + 2.23606797749979 * r + (5.0 / 3.0) * dist) * exp(-2.23606797749979 * r);
-    }
-    if (i == j) v += diag;
-    Kout[e] = v;
+  // warp w evaluates rows w, w + nwarps, ...: lanes stride over the columns j <= i (no index decoding, row data reused)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (TILED) {
+    const int ld = n | 1;                       // odd row stride: the mirrored (column) writes are bank-conflict free
+    for (int i = warp; i < n; i += nwarps)
+      for (int j = lane; j <= i; j += 32) {
+        double v = cov_entry(Xs, nhw, d, i, j, c0, sf2, kind);
+        if (i == j) v += diag;
+        tile[i * ld + j] = v;
+        tile[j * ld + i] = v;
+      }
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarps)      // coalesced: a warp writes consecutive addresses of one row
+      for (int j = lane; j < n; j += 32) Kout[int64_t(i) * n + j] = tile[i * ld + j];
+  } else {
+    // larger n: no tile; the mirrored store goes to a different row per lane, but the whole matrix is L2-resident
+    // (126 MB L2) until complete, so the partial sectors merge there and HBM still sees n^2 x 8 B per matrix
+    for (int i = warp; i < n; i += nwarps)
+      for (int j = lane; j <= i; j += 32) {
+        double v = cov_entry(Xs, nhw, d, i, j, c0, sf2, kind);
+        if (i == j) v += diag;
+        Kout[int64_t(i) * n + j] = v;
+        Kout[int64_t(j) * n + i] = v;
+      }
   }
 }
 
