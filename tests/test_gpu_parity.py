@@ -522,3 +522,31 @@ def test_full_size_cfg3_and_cfg4_properties(handle, dev):
     nll2, st2 = handle.nlml(nz['Xn'][:16].contiguous(), nz['Yn'][:16].contiguous(), w['theta'][:16].contiguous())
     assert torch.equal(nll2, nll[:16])
     assert torch.equal(handle.argmin(nll2)[1], bi[:16]) and torch.equal(bi, nll.argmin(dim=1))
+
+
+@pytest.mark.parametrize('n,bad_row', [(64, 5), (64, 60), (128, 77), (100, 99)])
+def test_k3_lookahead_kernel_reports_failures_without_hanging(handle, dev, n, bad_row):
+    """Non-positive pivot inside the look-ahead kernel (n > 48): every warp role must leave its barrier protocol.  A
+    duplicated data point with zero noise and a slightly NEGATIVE diagonal shift makes the leading minor of order
+    bad_row + 1 robustly indefinite (an exactly singular one can come out as a tiny positive pivot)."""
+    rng = np.random.default_rng(n + bad_row)
+    X = rng.uniform(-1, 1, (2, n, 3)); y = rng.standard_normal((2, n))
+    X[0, bad_row] = X[0, bad_row - 3]                       # problem 0 is singular, problem 1 is fine
+    nz = handle.normalise(T(X, dev), T(y, dev))
+    theta = np.tile(np.array([0.0, 0.0, 0.0, 0.0, -400.0]), (2, 1, 1))
+    theta[1, 0, 4] = -2.0
+    for k3 in (0, 2):
+        handle.set_option('k3_path', k3)
+        nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(theta, dev), jitter=-1e-3)
+        handle.set_option('k3_path', 0)
+        torch.cuda.synchronize()
+        st = st.cpu().numpy()
+        # the shifted matrix goes indefinite at or before the duplicated row; LAPACK's dpotrf on the oracle's matrix says where
+        from scipy.linalg import lapack
+        _, _, _, _, Xn0, _ = O.normalise(X[0], y[0].reshape(-1, 1))
+        W, sf2, sn2 = O.unpack_theta(theta[0, 0], 3)
+        K0 = O.cov_mat('RBF', Xn0, W, sf2) + (sn2 - 1e-3) * np.eye(n)
+        info = lapack.dpotrf(K0, lower=1)[1]
+        assert 0 < info <= bad_row + 1
+        assert st[0, 0] == info and st[1, 0] == 0, (k3, st, info)
+        assert np.isnan(float(nll[0, 0])) and np.isfinite(float(nll[1, 0]))
