@@ -1,7 +1,7 @@
 """ctypes binding of libgprto.so (C ABI: include/gprto.h).  No fallback: a missing library is an error."""
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GPRTO_LIB', os.path.join(HERE, 'libgprto.so'))   # GPRTO_LIB: A/B builds of the same ABI

@@ -356,7 +356,7 @@ def test_host_entry_matches_device_entry(handle, dev):
 
 
 def test_invalid_arguments_are_rejected(handle, dev):
-    from gp_rto_ei_b200._lib import GprtoError, EINVAL, EUNSUPPORTED
+    from gp_rto_ei_b200._lib import GprtoError, EINVAL
     w = workloads.cfg3_torch(dev, seed=1, B=2, n=16, d=2, m=8)
     gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
     with pytest.raises(GprtoError) as e:
