@@ -26,7 +26,16 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-METRIC = 'GP posterior+EI evals/sec (FP64, batched)'
+def _baseline_metric():
+    """The metric name is BASELINE.json's, verbatim."""
+    try:
+        with open(os.path.join(REPO, 'BASELINE.json')) as fh:
+            return json.load(fh)['metric']
+    except Exception:
+        return 'GP posterior+EI evals/sec (FP64, batched) at 1/2/4/8 B200; % of roofline'
+
+
+METRIC = _baseline_metric()
 UNIT = 'evals/s'
 
 
