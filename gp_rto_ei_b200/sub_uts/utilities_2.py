@@ -134,12 +134,13 @@ class GP_model:
 
     # ---------------------------------------------------------------- NLML (utilities_2.py:92-114)
     def negative_loglikelihood(self, hyper, X, Y):
-        Xd = self._Xn if X is self.X_norm else _dev(X, self._h)
+        Xd = (self._Xn if X is self.X_norm else _dev(X, self._h)).unsqueeze(0).contiguous()
         Yd = _dev(np.asarray(Y, dtype=float).reshape(1, -1), self._h)
-        th = _dev(np.asarray(hyper, dtype=float).reshape(1, 1, -1), self._h)
-        nll, st = self._h.nlml(Xd.unsqueeze(0).contiguous(), Yd, th, jitter=_JITTER)
-        self._h.raise_on_failure(st, 'negative_loglikelihood')
-        return float(nll[0, 0])
+        nll, st = self._h.nlml_indexed_host(Xd, Yd, np.zeros(1, dtype=np.int32), np.asarray(hyper, dtype=float).reshape(1, -1),
+                                            jitter=_JITTER)
+        if st[0]:
+            raise np.linalg.LinAlgError('Matrix is not positive definite (leading minor of order %d)' % st[0])   # as :107
+        return float(nll[0])
 
     # ---------------------------------------------------------------- fit (utilities_2.py:120-177)
     def determine_hyperparameters(self, noise=None, _theta=None):
@@ -193,9 +194,11 @@ class GP_model:
     def GP_inference_batch(self, Xq):
         """Posterior at m points at once: Xq[m, d] -> (mean[m, ny], var[m, ny]), de-normalised, var clamped at 0."""
         Xq = np.asarray(Xq, dtype=float).reshape(-1, self.nx_dim)
-        cand = _dev(Xq, self._h).unsqueeze(0).expand(self.ny_dim, Xq.shape[0], self.nx_dim).contiguous()
-        out = self._h.posterior_acq(self._gp, cand, None, None, api.ACQ_MEAN, want=('mean', 'var'))
-        return out['mean'].T.cpu().numpy(), out['var'].T.cpu().numpy()
+        # host entry of K4: one synchronous C call, no torch objects on the way (this is also the scalar path of
+        # GP_inference_np, ~45 us per call)
+        out = self._h.posterior_acq_host_np(self._gp, np.broadcast_to(Xq, (self.ny_dim,) + Xq.shape), None, None, api.ACQ_MEAN,
+                                            want=('mean', 'var'))
+        return out['mean'].T, out['var'].T
 
     def GP_inference_np(self, x):
         if self.GP_casadi:

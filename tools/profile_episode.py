@@ -29,3 +29,19 @@ episode(1, 2)      # warm-up (library load, kernels)
 t0 = time.time(); episode(0); print('episode wall %.2f s' % (time.time() - t0))
 pr = cProfile.Profile(); pr.enable(); episode(0); pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(28)
+
+# scalar API latency (the reference needs ~50 us per GP_inference_np call, SURVEY.md par. 6)
+rng = np.random.default_rng(0)
+X = rng.uniform(-1, 1, (24, 2)); Y = np.sin(X.sum(1, keepdims=True))
+gp = u2.GP_model(X, Y, 'RBF', multi_hyper=2, var_out=True, noise=None)
+x = np.array([0.1, 0.2])
+for _ in range(50):
+    gp.GP_inference_np(x)
+t0 = time.perf_counter()
+for _ in range(2000):
+    gp.GP_inference_np(x)
+print('GP_inference_np scalar call: %.1f us' % ((time.perf_counter() - t0) / 2000 * 1e6))
+t0 = time.perf_counter()
+for _ in range(500):
+    gp.negative_loglikelihood(gp.hypopt[:, 0], gp.X_norm, gp.Y_norm[:, 0])
+print('negative_loglikelihood scalar call: %.1f us' % ((time.perf_counter() - t0) / 500 * 1e6))
