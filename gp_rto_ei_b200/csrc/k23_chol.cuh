@@ -12,7 +12,7 @@ constexpr int CH_MAXD = 16;
 
 __host__ __device__ inline int ch_ld(int n) { return n | 1; }
 inline size_t ch_smem_bytes(int n, int d) {
-  return sizeof(double) * (size_t(n) * ch_ld(n) + size_t(n) * d + 2 * size_t(n) + 2 * CH_MAXD + 8);
+  return sizeof(double) * (size_t(n) * ch_ld(n) + size_t(n) * d + 3 * size_t(n) + 2 * CH_MAXD + 8);
 }
 
 // K_ij = exp(2 theta_sf + sum_dd (x_i - x_j)^2 * nhw_dd),  nhw_dd = -1/(2 W_dd) = -0.5 exp(-2 theta_dd).
@@ -27,56 +27,61 @@ __device__ __forceinline__ void ch_stage_inputs(const double* __restrict__ Xn, c
 
 __device__ __forceinline__ void ch_build_K(const double* Xs, const double* nhw, int n, int d, double c0,
                                            double diag_add, double* A, int ld) {
-  // lower triangle incl. diagonal, mirrored into the upper triangle
-  const int total = n * (n + 1) / 2;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    int i = int((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-    while (i * (i + 1) / 2 > e) --i;
-    while ((i + 1) * (i + 2) / 2 <= e) ++i;
-    const int j = e - i * (i + 1) / 2;
-    double acc = c0;
-    for (int dd = 0; dd < d; ++dd) {
-      const double df = Xs[i * d + dd] - Xs[j * d + dd];
-      acc = fma(df * df, nhw[dd], acc);
+  // lower triangle incl. diagonal, mirrored into the upper triangle; warp w takes rows w, w + nwarps, ...
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < n; i += nwarps)
+    for (int j = lane; j <= i; j += 32) {
+      double acc = c0;
+      for (int dd = 0; dd < d; ++dd) {
+        const double df = Xs[i * d + dd] - Xs[j * d + dd];
+        acc = fma(df * df, nhw[dd], acc);
+      }
+      double v = exp_fast(acc);
+      if (i == j) v += diag_add;
+      A[i * ld + j] = v;
+      A[j * ld + i] = v;
     }
-    double v = exp_fast(acc);
-    if (i == j) v += diag_add;
-    A[i * ld + j] = v;
-    A[j * ld + i] = v;
-  }
 }
 
-// In-place lower Cholesky of A (n x n, stride ld) by the whole CTA.  Returns via *info the dpotrf code.
-// logdet accumulates 2*sum log L_ii.
-__device__ __forceinline__ void ch_cholesky(double* A, int n, int ld, int* s_info, double* s_logdet) {
+// In-place lower Cholesky of A (n x n, stride ld) by the whole CTA, ONE barrier per column: the column is not scaled
+// while the factorisation runs - the rank-1 update uses the unscaled column and 1/pivot
+// (A_ij -= A_ik A_jk / piv), 1/sqrt(pivot) goes to rinv[k], and all columns are scaled in one parallel pass at the
+// end.  The diagonal keeps the PIVOTS until then (log det = sum log pivots, in parallel).  On exit: strictly lower
+// triangle = L, diagonal = L_kk, rinv[k] = 1/L_kk.  *s_info is the dpotrf code.
+__device__ __forceinline__ void ch_cholesky(double* A, int n, int ld, double* rinv, int* s_info, double* s_logdet) {
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) { *s_info = 0; *s_logdet = 0.0; }
   __syncthreads();
+  const int tr = tid & 15, tc = tid >> 4;
   for (int k = 0; k < n; ++k) {
-    if (tid == 0) {
-      const double piv = A[k * ld + k];
-      if (!(piv > 0.0)) {
-        if (*s_info == 0) *s_info = k + 1;
-        A[k * ld + k] = CUDART_NAN;
-      } else {
-        const double l = sqrt(piv);
-        A[k * ld + k] = l;
-        *s_logdet += 2.0 * log(l);
-      }
+    const double piv = A[k * ld + k];               // final since the previous column's barrier
+    if (!(piv > 0.0)) {                             // uniform: every thread reads the same value
+      if (tid == 0) *s_info = k + 1;
+      __syncthreads();
+      return;
     }
-    __syncthreads();
-    if (*s_info != 0) return;                       // uniform: every thread sees the same flag
-    const double lkk = A[k * ld + k];
-    for (int i = k + 1 + tid; i < n; i += nt) A[i * ld + k] /= lkk;
-    __syncthreads();
+    const double r = rsqrt_fast(piv);
+    if (tid == 0) rinv[k] = r;
+    const double ip = r * r;                        // 1 / pivot
     // trailing update of the lower triangle: 16 x 16 thread grid, rows/cols strided by 16
-    const int tr = tid & 15, tc = tid >> 4;
     for (int i = k + 1 + tr; i < n; i += 16) {
-      const double lik = A[i * ld + k];
+      const double lik = A[i * ld + k] * ip;
       for (int j = k + 1 + tc; j <= i; j += 16) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
     }
     __syncthreads();
   }
+  double lg = 0.0;
+  for (int k = tid; k < n; k += nt) lg += log(A[k * ld + k]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, off);
+  if ((tid & 31) == 0) atomicAdd(s_logdet, lg);
+  __syncthreads();                                  // rinv complete, pivots read
+  for (int e = tid; e < n * n; e += nt) {
+    const int i = e / n, k = e - i * n;
+    if (k < i) A[i * ld + k] *= rinv[k];
+    else if (k == i) A[i * ld + i] *= rinv[i];      // pivot -> L_ii
+  }
+  __syncthreads();
 }
 
 // K3 generic: one CTA per (GP, start).
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   double* Xs = A + size_t(n) * ld;
   double* z = Xs + n * d;
   double* nhw = z + 2 * n;
+  double* rinv = z + n;                      // second half of the 2n scratch
   __shared__ int s_info;
   __shared__ double s_logdet;
   const int64_t bs = blockIdx.x;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   const double sn2 = exp(2.0 * theta[d + 1]);
   ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], sn2 + jitter, A, ld);
   __syncthreads();
-  ch_cholesky(A, n, ld, &s_info, &s_logdet);
+  ch_cholesky(A, n, ld, rinv, &s_info, &s_logdet);
   __syncthreads();
   if (s_info != 0) {
     if (threadIdx.x == 0) { nll[bs] = CUDART_NAN; status[bs] = s_info; }
@@ -205,7 +211,8 @@ __global__ void __launch_bounds__(CH_THREADS) factor_generic_kernel(int n, int d
   double* Xs = A + size_t(n) * ld;
   double* y = Xs + n * d;
   double* z = y + n;
-  double* nhw = z + n;
+  double* rinv = z + n;
+  double* nhw = rinv + n;
   __shared__ int s_info;
   __shared__ double s_logdet;
   const int64_t b = blockIdx.x;
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(CH_THREADS) factor_generic_kernel(int n, int d
   __syncthreads();
   ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], exp(2.0 * theta[d + 1]) + jitter, A, ld);
   __syncthreads();
-  ch_cholesky(A, n, ld, &s_info, &s_logdet);
+  ch_cholesky(A, n, ld, rinv, &s_info, &s_logdet);
   __syncthreads();
   double* out = invK + b * int64_t(n) * n;
   if (s_info != 0) {
@@ -229,28 +236,41 @@ __global__ void __launch_bounds__(CH_THREADS) factor_generic_kernel(int n, int d
   // triangle, U[c][i] = X[i][c] for i > c.  Threads only read L (lower + diagonal) and their own row of U.
   // pass 1: strictly-lower part of L^-1 into the strictly-upper triangle; the diagonal 1/L_cc into z-free scratch
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    const double xcc = 1.0 / A[c * ld + c];
+    const double xcc = rinv[c];
     for (int i = c + 1; i < n; ++i) {
-      double acc = A[i * ld + c] * xcc;                        // L_ic * X_cc
-      for (int k = c + 1; k < i; ++k) acc = fma(A[i * ld + k], A[c * ld + k], acc);   // L_ik * X_kc
-      A[c * ld + i] = -acc / A[i * ld + i];
+      // X_ic = -(L_ic X_cc + sum_{c<k<i} L_ik X_kc) / L_ii ; four independent partial sums hide the FMA latency
+      double a0 = A[i * ld + c] * xcc, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = c + 1;
+      for (; k + 3 < i; k += 4) {
+        a0 = fma(A[i * ld + k], A[c * ld + k], a0);
+        a1 = fma(A[i * ld + k + 1], A[c * ld + k + 1], a1);
+        a2 = fma(A[i * ld + k + 2], A[c * ld + k + 2], a2);
+        a3 = fma(A[i * ld + k + 3], A[c * ld + k + 3], a3);
+      }
+      for (; k < i; ++k) a0 = fma(A[i * ld + k], A[c * ld + k], a0);
+      A[c * ld + i] = -((a0 + a1) + (a2 + a3)) * rinv[i];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < n; c += blockDim.x) A[c * ld + c] = 1.0 / A[c * ld + c];
+  for (int c = threadIdx.x; c < n; c += blockDim.x) A[c * ld + c] = rinv[c];
   __syncthreads();
   // now U (upper incl. diagonal) holds X' where X = L^-1:  U[c][i] = X[i][c], i >= c.
   // invK[i][j] = sum_{k >= max(i,j)} X[k][i] X[k][j] = sum_k U[i][k] U[j][k]
-  const int total = n * (n + 1) / 2;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    int i = int((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-    while (i * (i + 1) / 2 > e) --i;
-    while ((i + 1) * (i + 2) / 2 <= e) ++i;
-    const int j = e - i * (i + 1) / 2;            // j <= i
-    double acc = 0.0;
-    for (int k = i; k < n; ++k) acc = fma(A[i * ld + k], A[j * ld + k], acc);
-    out[int64_t(i) * n + j] = acc;
-    out[int64_t(j) * n + i] = acc;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nwarps)
+      for (int j = lane; j <= i; j += 32) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = i;
+        for (; k + 1 < n; k += 2) {
+          a0 = fma(A[i * ld + k], A[j * ld + k], a0);
+          a1 = fma(A[i * ld + k + 1], A[j * ld + k + 1], a1);
+        }
+        if (k < n) a0 = fma(A[i * ld + k], A[j * ld + k], a0);
+        const double acc = a0 + a1;
+        out[int64_t(i) * n + j] = acc;
+        out[int64_t(j) * n + i] = acc;
+      }
   }
   // alpha = X' (X y):  z = X y (z_k = sum_{i<=k} X[k][i] y_i = sum_i U[i][k] y_i), alpha_i = sum_{k>=i} U[i][k] z_k
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
