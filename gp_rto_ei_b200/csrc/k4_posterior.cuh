@@ -21,15 +21,9 @@ struct K4Params {
   int64_t* part_idx;
 };
 
-#ifndef K4_UNROLL_U
-#define K4_UNROLL_U 1
-#endif
-constexpr int K4_UNROLL = K4_UNROLL_U;   // tiles of the 4-tile group processed together (ILP vs registers)
 constexpr int K4_WARPS = 4;
 constexpr int K4_THREADS = K4_WARPS * 32;
-#ifndef K4_MINB
-#define K4_MINB 4
-#endif
+constexpr int K4_MINB = 4;               // CTAs per SM asked of ptxas for NB <= 8 (128 registers; 3, 5 and 6 measured the same)
 
 // Data index handled by k-step s on a lane with threadID-in-group t: within an 8-block the four
 // lanes of a quad own {2t, 2t+1}, which is exactly the pair of output columns the same lane holds in
@@ -47,7 +41,7 @@ __host__ __device__ constexpr size_t k4_smem_bytes() {
 
 // One CTA = one GP x one chunk of its candidates.  Each warp walks the chunk 32 candidates at a time as
 // four 8-candidate DMMA tiles:
-//   A fragment (8 candidates x 4 data points)  = cross-covariances k*, computed in registers (16*... exps/lane)
+//   A fragment (8 candidates x 4 data points)  = cross-covariances k*, computed in registers (2 NB exps per lane)
 //   B fragment (4 data points x 8 rows of M)    = folded inverse M = tril(invK + invK') - diag(invK), staged once
 //                                                 per CTA in shared memory in fragment order (conflict-free LDS.64)
 //   C accumulators                              = (M k*) for the lane's own data points
@@ -138,7 +132,7 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
     }
 
     double q_mine = 0.0, m_mine = 0.0;
-#pragma unroll K4_UNROLL
+#pragma unroll 1                         // one tile at a time: two at once spill (measured slower)
     for (int u = 0; u < 4; ++u) {
       double x[D];
 #pragma unroll
