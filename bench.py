@@ -354,7 +354,7 @@ def run_ours(args):
 
     # ---- parity sample against the oracle (outside the timed region)
     from oracle import gp_oracle as O
-    npar = 8
+    npar = 64
     worst = {'mean': 0.0, 'var': 0.0, 'score': 0.0, 'argmin_mismatch': 0}
     Xh, yh, th = w['X'][:npar].cpu().numpy(), w['y'][:npar].cpu().numpy(), w['theta'][:npar].cpu().numpy()
     ch, fh = cand[:npar].cpu().numpy(), f_best[:npar].cpu().numpy()
