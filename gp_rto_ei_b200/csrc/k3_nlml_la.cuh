@@ -27,9 +27,11 @@
 
 namespace gprto {
 
+// warps per CTA: 1 panel + W-1 update warps.  8 for every size: at NT = 8..14 that is more warps (and fewer tiles, i.e.
+// registers, per warp) than the NT/2 of the plain register kernel, which buys a third resident CTA at NT = 8.
 template <int NT>
 struct K3LA {
-  static constexpr int W = NT / 2;                 // warps per CTA (1 panel + update warps [+ 1 idle])
+  static constexpr int W = 8;
   // (idling the warp that shares the panel warp's scheduler was measured slower: 7.5e6 vs 8.3e6 evals/s at n = 128)
   static constexpr int IDLE = 0;
   static constexpr int UW = W - 1 - IDLE;
@@ -155,7 +157,7 @@ __device__ __forceinline__ void k3_diag_tile_lean(double* tile, int ldp, double*
 }
 
 template <int NT, int DT>
-__global__ void __launch_bounds__(16 * NT, 2)
+__global__ void __launch_bounds__(32 * K3LA<NT>::W, (NT <= 8 ? 3 : 2))      // 256 threads: <= 85 / 128 registers
 k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const double* __restrict__ Yn,
                   const double* __restrict__ theta_all, double jitter, double* __restrict__ nll,
                   int32_t* __restrict__ status, const int32_t* __restrict__ gidx) {
@@ -392,7 +394,7 @@ int launch_k3la_d(int64_t B, int S, int n, int d, const double* Xn, const double
     cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k3_nlml_la_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
+  k3_nlml_la_kernel<NT, DT><<<(unsigned)(B * S), 32 * K3LA<NT>::W, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
@@ -407,14 +409,16 @@ int launch_k3la(int64_t B, int S, int n, int d, const double* Xn, const double* 
   return launch_k3la_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
-// Look-ahead kernel where it measured faster than k3_nlml_tile_kernel (B200, d = 3: n = 64: 3.21e7 vs 3.08e7 evals/s,
-// n = 80: 1.81e7 vs 2.06e7 (so not used), n = 96: 1.35e7 vs 1.07e7, n = 112: 1.06e7 vs 7.4e6, n = 128: 8.4e6 vs 5.9e6);
-// returns GPRTO_EUNSUPPORTED otherwise (the caller falls back to launch_nlml_reg).
+// Look-ahead kernel where it measured faster than k3_nlml_tile_kernel (B200, d = 3, evals/s look-ahead vs plain):
+// n = 48: 4.9e7 vs 4.6e7, n = 64: 3.4e7 vs 3.1e7, n = 80: 1.9e7 vs 2.1e7 (so not used), n = 96: 1.4e7 vs 1.1e7,
+// n = 112: 1.1e7 vs 7.4e6, n = 128: 8.4e6 vs 5.9e6; returns GPRTO_EUNSUPPORTED otherwise (the caller falls back to
+// launch_nlml_reg).
 int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                    double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
-  if (n > K3R_MAXN || d > K3R_MAXD || n <= 48) return GPRTO_EUNSUPPORTED;
+  if (n > K3R_MAXN || d > K3R_MAXD || n <= 32) return GPRTO_EUNSUPPORTED;
   const int nt = (n + 15) / 16 * 2;
   switch (nt) {
+    case 6: return launch_k3la<6>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     case 8: return launch_k3la<8>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     case 12: return launch_k3la<12>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     case 14: return launch_k3la<14>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
