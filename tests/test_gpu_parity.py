@@ -550,3 +550,41 @@ def test_k3_lookahead_kernel_reports_failures_without_hanging(handle, dev, n, ba
         assert 0 < info <= bad_row + 1
         assert st[0, 0] == info and st[1, 0] == 0, (k3, st, info)
         assert np.isnan(float(nll[0, 0])) and np.isfinite(float(nll[1, 0]))
+
+
+def test_k4_nan_candidate_and_single_candidate_batches(handle, dev):
+    """numpy.argmin semantics on the device: a NaN score wins (first one); and B = 4096 GPs with m = 1 candidate each."""
+    w = workloads.cfg3_torch(dev, seed=77, B=4096, n=64, d=3, m=40)
+    gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
+    cand = w['cand'].clone()
+    cand[5, 17, 0] = float('nan'); cand[5, 30, 1] = float('nan')
+    out = handle.posterior_acq(gd, cand, None, w['f_best'], 3, want=('score', 'best'))
+    sc = out['score'].cpu().numpy()
+    assert np.isnan(sc[5, 17]) and np.isnan(sc[5, 30]) and int(out['best_idx'][5]) == 17 == int(np.argmin(sc[5]))
+    assert np.isnan(float(out['best_score'][5]))
+    others = np.delete(np.arange(4096), 5)
+    assert np.array_equal(out['best_idx'].cpu().numpy()[others], np.argmin(sc[others], axis=1))
+    one = handle.posterior_acq(gd, w['cand'][:, :1].contiguous(), None, w['f_best'], 2, want=('score', 'best'))
+    assert bool((one['best_idx'] == 0).all()) and torch.equal(one['best_score'], one['score'][:, 0])
+
+
+@pytest.mark.parametrize('n,d', [(100, 6), (128, 8), (60, 1), (40, 5)])
+def test_k3_lookahead_kernel_generic_dimension(handle, dev, n, d):
+    """The look-ahead kernel's run-time-d path (d other than 2 and 3) against the oracle and the other two K3 kernels."""
+    rng = np.random.default_rng(10 * n + d)
+    X = rng.uniform(-1, 1, (2, n, d)); y = np.sin(X.sum(-1)) + 0.05 * rng.standard_normal((2, n))
+    th = np.concatenate([rng.uniform(-0.3, 0.8, (2, 3, d)), rng.uniform(-0.3, 0.3, (2, 3, 1)), rng.uniform(-3.4, -2.3, (2, 3, 1))], axis=2)
+    nz = handle.normalise(T(X, dev), T(y, dev))
+    res = []
+    for k3 in (0, 1, 2):
+        handle.set_option('k3_path', k3)
+        nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(th, dev))
+        handle.set_option('k3_path', 0)
+        assert int(st.abs().sum()) == 0
+        res.append(nll.cpu().numpy())
+    for b in range(2):
+        _, _, _, _, Xn, Yn = O.normalise(X[b], y[b].reshape(-1, 1))
+        for s in range(3):
+            ref = O.nlml(th[b, s], Xn, Yn[:, 0])
+            for r in res:
+                assert abs(r[b, s] - ref) <= 1e-9 * abs(ref), (n, d, b, s, r[b, s], ref)
