@@ -51,7 +51,8 @@ def _hyper_bounds(d, noise_i, y_std_i):
 
 def _fit_group(handle, Xn_dev, Yn_dev_rows, bounds_rows, multi_start):
     """Multistart SLSQP fit of G single-output GPs that share X (utilities_2.py:139-170), all starts of all GPs in
-    lock step.  Xn_dev[n,d]; Yn_dev_rows[G,n]; bounds_rows: list of (lb, ub).  Returns theta_opt[G, d+2]."""
+    lock step.  Xn_dev[n,d]; Yn_dev_rows[G,n]; bounds_rows: list of (lb, ub).  Returns theta_opt[G, d+2] and, per GP, the
+    multistart record dict(localval[S], localsol[S,d+2], minindex) - the reference's `localval` / `localsol` / `minindex`."""
     n, d = Xn_dev.shape
     G = Yn_dev_rows.shape[0]
     sob = sobol_seq.i4_sobol_generate(d + 2, multi_start)
@@ -76,18 +77,20 @@ def _fit_group(handle, Xn_dev, Yn_dev_rows, bounds_rows, multi_start):
 
     res = slsqp_batch.minimize_batch(fun_batch, x0s, bnds, ftol=1e-12, maxiter=10000, inst_ids=list(range(len(x0s))))
     theta = np.empty((G, d + 2))
+    info = []
     for g in range(G):
         vals = np.array([res[g * multi_start + j].fun for j in range(multi_start)])
         best = int(np.argmin(vals))                                      # first minimum wins (utilities_2.py:166)
         theta[g] = res[g * multi_start + best].x
-    return theta
+        info.append(dict(localval=vals, localsol=np.stack([res[g * multi_start + j].x for j in range(multi_start)]), minindex=best))
+    return theta, info
 
 
 class GP_model:
     """Gaussian process with SE-ARD kernel, fitted by NLML multistart and evaluated on the GPU.
     Constructor arguments and attributes as the reference's GP_model (utilities_2.py:28-44)."""
 
-    def __init__(self, X, Y, kernel, multi_hyper, var_out=True, noise=None, GP_casadi=False, _theta=None):
+    def __init__(self, X, Y, kernel, multi_hyper, var_out=True, noise=None, GP_casadi=False, _theta=None, _fit_info=None):
         self.X, self.Y, self.kernel = X, Y, kernel
         self.n_point, self.nx_dim = X.shape[0], X.shape[1]
         self.ny_dim = Y.shape[1]
@@ -105,6 +108,7 @@ class GP_model:
         self.X_norm, self.Y_norm = (X - self.X_mean) / self.X_std, (Y - self.Y_mean) / self.Y_std
         self._Xn = _dev(self.X_norm, self._h)                      # [n, d]
         self._Yn = _dev(self.Y_norm.T, self._h)                    # [ny, n]
+        self._fit_info = _fit_info                                 # per output: localval / localsol / minindex of the multistart
         self.hypopt, self.invKopt = self.determine_hyperparameters(noise, _theta=_theta)
         self.meanfcn, self.varfcn = self.GP_predictor()
 
@@ -155,7 +159,7 @@ class GP_model:
                     # the reference mutates lb/ub in place, so a pinned noise bound persists for later outputs
                     lb, ub = _hyper_bounds(d, known, self.Y_std[i] if known is not None else None)
                 bounds_rows.append((lb.copy(), ub.copy()))
-            theta = _fit_group(self._h, self._Xn, self._Yn, bounds_rows, self.multi_hyper)
+            theta, self._fit_info = _fit_group(self._h, self._Xn, self._Yn, bounds_rows, self.multi_hyper)
         else:
             theta = np.asarray(_theta, dtype=float).reshape(ny, d + 2)
         hypopt = np.ascontiguousarray(theta.T)                      # (d+2, ny) as the reference
@@ -487,8 +491,8 @@ def _fit_shared_X(X, Ys, noises, multi_hyper, var_outs):
         y_std = np.std(Y, axis=0)
         rows.append(((Y - np.mean(Y, axis=0)) / y_std)[:, 0])
         bounds_rows.append(_hyper_bounds(d, nz, y_std[0] if nz is not None else None))
-    theta = _fit_group(h, _dev(Xn, h), _dev(np.stack(rows), h), bounds_rows, multi_hyper)
-    return [GP_model(X, Y, 'RBF', multi_hyper=multi_hyper, var_out=vo, noise=nz, _theta=theta[g])
+    theta, info = _fit_group(h, _dev(Xn, h), _dev(np.stack(rows), h), bounds_rows, multi_hyper)
+    return [GP_model(X, Y, 'RBF', multi_hyper=multi_hyper, var_out=vo, noise=nz, _theta=theta[g], _fit_info=[info[g]])
             for g, (Y, nz, vo) in enumerate(zip(Ys, noises, var_outs))]
 
 

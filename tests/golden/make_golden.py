@@ -16,6 +16,8 @@ Files written
   rto_simple.npz    three short seeded episodes of the reference's ITR_GP_RTO on the toy problem (trajectories, TR radii,
                     backtrack flags).
   rto_wo.npz        the same for the Williams-Otto configuration (2 constraint GPs, ellipse start sampling, model prior).
+  fit_starts.npz    per-start results (x0, res.x, res.fun, nit, status) and the selected start index of the reference's
+                    multistart on the six pickle data sets, free and known noise.
   ragged.npz        edge cases: n=1, n=2, n=7 (not a multiple of 8), d=1 and d=5, zero variance (candidate on a
                     noise-free data point), far-tail EI.
 """
@@ -121,6 +123,37 @@ def pickle_gps():
         print('pickle GP', g, path, 'n=%d' % X.shape[0], 'cond=%.2e' % out[f'cond{g}'], 'hyp', gp.hypopt.ravel())
     out['count'] = len(srcs)
     np.savez_compressed(os.path.join(HERE, 'pickle_gps.npz'), **out)
+
+
+def fit_starts():
+    """Per-start outcome of the reference's hyper-parameter multistart (utilities_2.py:156-167) on the six pickle data
+    sets: res.x / res.fun of every SLSQP start and the index np.argmin selects.  Recorded by wrapping the `minimize`
+    name the reference module calls (the module itself is not modified); known-noise variant included (bounds :149-154)."""
+    src = np.load(os.path.join(HERE, 'pickle_gps.npz'))
+    out = {'count': int(src['count'])}
+    orig = ref.minimize
+    for g in range(int(src['count'])):
+        X, Y = src[f'X{g}'], src[f'Y{g}']
+        for tag, noise in (('', None), ('_kn', 1e-3)):
+            log = []
+
+            def rec(fun, x0, *a, **k):
+                r = orig(fun, x0, *a, **k)
+                log.append((np.array(x0, dtype=float), np.array(r.x, dtype=float), float(np.asarray(r.fun).reshape(-1)[0]), int(r.nit), int(r.status)))
+                return r
+            ref.minimize = rec
+            try:
+                gp = ref.GP_model(X, Y, 'RBF', multi_hyper=4, var_out=True, noise=noise)
+            finally:
+                ref.minimize = orig
+            vals = np.array([l[2] for l in log])
+            out.update({f'x0{tag}{g}': np.stack([l[0] for l in log]), f'localsol{tag}{g}': np.stack([l[1] for l in log]),
+                        f'localval{tag}{g}': vals, f'nit{tag}{g}': np.array([l[3] for l in log]),
+                        f'status{tag}{g}': np.array([l[4] for l in log]), f'minindex{tag}{g}': int(np.argmin(vals)),
+                        f'hypopt{tag}{g}': gp.hypopt.copy()})
+            assert np.array_equal(gp.hypopt[:, 0], log[int(np.argmin(vals))][1])
+            print('fit_starts GP', g, tag or 'free', 'localval', vals, 'minindex', int(np.argmin(vals)))
+    np.savez_compressed(os.path.join(HERE, 'fit_starts.npz'), **out)
 
 
 def cfg3_small():
@@ -303,6 +336,7 @@ if __name__ == '__main__':
         globals()[sys.argv[1]]()
         sys.exit(0)
     pickle_gps()
+    fit_starts()
     cfg3_small()
     cfg4_small()
     ragged()
