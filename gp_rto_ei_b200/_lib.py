@@ -22,6 +22,7 @@ PROTOTYPES = {
     'gprto_limits': (c_int, [POINTER(c_int64)]),
     'gprto_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
     'gprto_launch_count': (c_int64, [c_void_p]),
+    'gprto_order_after': (c_int, [c_void_p, _P]),
     'gprto_normalise': (c_int, [c_void_p, c_int64, c_int, c_int] + [_P] * 8 + [_P]),
     'gprto_cov_se_ard': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, _P, _P, c_int, c_double, _P, _P]),
     'gprto_nlml': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, _P, _P, _P, c_double, _P, _P, _P]),

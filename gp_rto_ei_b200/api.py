@@ -55,6 +55,11 @@ class Handle:
     def _new(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    def _order_host_call(self):
+        """The *_host entry points run on handle-private streams: fence them behind torch's current stream, which
+        produced their device-resident inputs (include/gprto.h: gprto_order_after)."""
+        _lib.check(self.lib.gprto_order_after(self._h, self._stream()), 'gprto_order_after')
+
     def set_option(self, name, value):
         _lib.check(self.lib.gprto_set_option(self._h, name.encode(), int(value)), 'gprto_set_option')
 
@@ -106,6 +111,7 @@ class Handle:
         k = gp_index.shape[0]
         nll = np.empty(k, dtype=np.float64)
         st = np.empty(k, dtype=np.int32)
+        self._order_host_call()
         _lib.check(self.lib.gprto_nlml_indexed_host(self._h, G, k, n, d, _ptr(Xn), _ptr(Yn), gp_index.ctypes.data, theta.ctypes.data,
                                                     float(jitter), nll.ctypes.data, st.ctypes.data), 'gprto_nlml_indexed_host')
         return nll, st
@@ -121,6 +127,7 @@ class Handle:
         if 'best' in want:
             out['best_score'], out['best_idx'] = np.empty(B), np.empty(B, dtype=np.int64)
         g = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        self._order_host_call()
         _lib.check(self.lib.gprto_posterior_acq_host(
             self._h, B, n, d, m, _ptr(gp['Xn']), _ptr(gp['invK']), _ptr(gp['alpha']), _ptr(gp['theta']), _ptr(gp['x_mean']),
             _ptr(gp['x_std']), _ptr(gp['y_mean']), _ptr(gp['y_std']), cand.ctypes.data, None if prior is None else prior.ctypes.data,
@@ -192,6 +199,7 @@ class Handle:
         for k, v in out_host.items():
             assert v.device.type == 'cpu' and v.is_contiguous(), k
         g = lambda k: _ptr(out_host.get(k))  # noqa: E731
+        self._order_host_call()
         _lib.check(self.lib.gprto_posterior_acq_host(
             self._h, B, n, d, m, _ptr(gp['Xn']), _ptr(gp['invK']), _ptr(gp['alpha']), _ptr(gp['theta']), _ptr(gp['x_mean']),
             _ptr(gp['x_std']), _ptr(gp['y_mean']), _ptr(gp['y_std']), _ptr(cand_host), _ptr(prior_host), _ptr(f_best), int(acq),
@@ -199,9 +207,10 @@ class Handle:
         return out_host
 
     def sample_candidates(self, centre, radius, m, shape=0, seed=0, idx=None):
-        """centre[B,d], radius[B] -> cand[B,m,d] (or [B,d] for the candidates idx[B])."""
+        """centre[B,d], radius[B] (shape 2: radius[B,d+1] = semi-axes + ball radius) -> cand[B,m,d] (or [B,d] for the
+        candidates idx[B])."""
         B, d = centre.shape
-        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B,), 'radius')
+        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B, d + 1) if shape == 2 else (B,), 'radius')
         out = self._new(B, d) if idx is not None else self._new(B, m, d)
         _lib.check(self.lib.gprto_sample_candidates(self._h, B, d, m, _ptr(centre), _ptr(radius), int(shape), int(seed), _ptr(idx),
                                                     _ptr(out), self._stream()), 'gprto_sample_candidates')
@@ -210,7 +219,7 @@ class Handle:
     def posterior_acq_sampled(self, gp, centre, radius, m, shape=0, seed=0, f_best=None, acq=ACQ_EI, out=None):
         """K4 with the m candidates of each GP generated inside the kernel; returns best_score[B], best_idx[B], best_x[B,d]."""
         B, n, d = gp['Xn'].shape
-        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B,), 'radius')
+        self._chk(centre, (B, d), 'centre'); self._chk(radius, (B, d + 1) if shape == 2 else (B,), 'radius')
         out = out or dict(best_score=self._new(B), best_idx=self._new(B, dtype=torch.int64), best_x=self._new(B, d))
         _lib.check(self.lib.gprto_posterior_acq_sampled(
             self._h, B, n, d, int(m), _ptr(gp['Xn']), _ptr(gp['invK']), _ptr(gp['alpha']), _ptr(gp['theta']), _ptr(gp['x_mean']),

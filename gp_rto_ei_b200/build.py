@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.environ.get('GPRTO_LIB_OUT', os.path.join(HERE, 'libgprto.so'))
-SOURCES = ['gprto_api.cu', 'k3_inst.cu', 'k4_inst_a.cu', 'k4_inst_b.cu', 'k4_inst_c.cu', 'k4_inst_d.cu']
+SOURCES = ['gprto_api.cu', 'k3_inst.cu', 'k2_inst.cu', 'k4_inst_a.cu', 'k4_inst_b.cu', 'k4_inst_c.cu', 'k4_inst_d.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
 
 

@@ -22,6 +22,9 @@ struct gprto_handle {
   int sm_count = 0;
   int k4_path = GPRTO_K4_AUTO;
   int k3_path = 0;
+  int k2_path = 0;
+  cudaEvent_t ev_order = nullptr;      // gprto_order_after: producer-stream fence for the *_host entry points
+  bool order_pending = false;
   int cov_kernel_kind = 0;
   std::atomic<int64_t> launches{0};
   // scratch (grown on demand)
@@ -277,6 +280,7 @@ int gprto_destroy(gprto_t* h) {
   if (h->small_pin) cudaFreeHost(h->small_pin);
   cudaFree(h->small_dev);
   if (h->small_stream) cudaStreamDestroy(h->small_stream);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -293,10 +297,20 @@ int gprto_set_option(gprto_t* h, const char* name, int64_t value) {
   if (!strcmp(name, "k4_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k4_path = int(value); return 0; }
   if (!strcmp(name, "cov_kernel")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->cov_kernel_kind = int(value); return 0; }
   if (!strcmp(name, "k3_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
+  if (!strcmp(name, "k2_path")) { if (value < 0 || value > 1) return GPRTO_EINVAL; h->k2_path = int(value); return 0; }
   return GPRTO_EINVAL;
 }
 
 int64_t gprto_launch_count(const gprto_t* h) { return h ? h->launches.load() : 0; }
+
+int gprto_order_after(gprto_t* h, void* stream) {
+  if (!h) return GPRTO_EINVAL;
+  DeviceGuard guard(h->device);
+  if (!h->ev_order) GPRTO_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+  GPRTO_CUDA(cudaEventRecord(h->ev_order, (cudaStream_t)stream));
+  h->order_pending = true;
+  return 0;
+}
 
 int gprto_normalise(gprto_t* h, int64_t B, int n, int d, const double* X, const double* Y, double* x_mean,
                     double* x_std, double* y_mean, double* y_std, double* Xn, double* Yn, void* stream) {
@@ -357,6 +371,7 @@ int gprto_nlml_indexed_host(gprto_t* h, int64_t G, int64_t k, int n, int d, cons
   }
   if (!h->small_stream) GPRTO_CUDA(cudaStreamCreateWithFlags(&h->small_stream, cudaStreamNonBlocking));
   cudaStream_t s = h->small_stream;
+  if (h->order_pending) { GPRTO_CUDA(cudaStreamWaitEvent(s, h->ev_order, 0)); h->order_pending = false; }
   memcpy(h->small_pin, theta_host, o_nll);
   memcpy(h->small_pin + o_idx, gp_index_host, size_t(k) * 4);
   GPRTO_CUDA(cudaMemcpyAsync(h->small_dev, h->small_pin, o_nll, cudaMemcpyHostToDevice, s));
@@ -364,7 +379,7 @@ int gprto_nlml_indexed_host(gprto_t* h, int64_t G, int64_t k, int n, int d, cons
   int rc = nlml_device(h, k, 1, n, d, Xn, Yn, reinterpret_cast<const double*>(h->small_dev), jitter,
                        reinterpret_cast<double*>(h->small_dev + o_nll), reinterpret_cast<int32_t*>(h->small_dev + o_st), s,
                        reinterpret_cast<const int32_t*>(h->small_dev + o_idx));
-  if (rc) return rc;
+  if (rc) { cudaStreamSynchronize(s); return rc; }
   GPRTO_CUDA(cudaMemcpyAsync(h->small_pin + o_nll, h->small_dev + o_nll, size_t(k) * 12, cudaMemcpyDeviceToHost, s));
   GPRTO_CUDA(cudaStreamSynchronize(s));
   memcpy(nll_host, h->small_pin + o_nll, size_t(k) * 8);
@@ -386,7 +401,12 @@ int gprto_factor(gprto_t* h, int64_t B, int n, int d, const double* Xn, const do
                  double jitter, double* invK, double* alpha, double* logdet, int32_t* status, void* stream) {
   if (!h || B <= 0 || n <= 0 || d <= 0 || !Xn || !Yn || !theta_opt || !invK || !alpha || !status) return GPRTO_EINVAL;
   if (d > CH_MAXD) return GPRTO_EUNSUPPORTED;
+  if (B > kMaxGridX) return GPRTO_EUNSUPPORTED;
   DeviceGuard guard(h->device);
+  if (h->k2_path == 0) {                    // register-tile / DMMA kernel for 32 < n <= 128
+    int rc = launch_factor_la(B, n, d, Xn, Yn, theta_opt, jitter, invK, alpha, logdet, status, (cudaStream_t)stream);
+    if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
+  }
   const size_t smem = ch_smem_bytes(n, d);
   if (smem > 227 * 1024) return GPRTO_EUNSUPPORTED;
   int rc = set_smem(factor_generic_kernel, smem);
@@ -433,6 +453,14 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m, con
   gps = std::min<int64_t>(gps, B);
   int rc = ensure_stage(h, in_per_gp * gps, std::max(out_per_gp, size_t(16)) * gps);
   if (rc) return rc;
+  if (h->order_pending) { GPRTO_CUDA(cudaStreamWaitEvent(h->st[1], h->ev_order, 0)); h->order_pending = false; }
+  // on any error below: let the copies already in flight into the caller's host buffers finish before returning
+  auto drain = [h](int code) { for (auto& st : h->st) cudaStreamSynchronize(st); return code; };
+#define GPRTO_CUDA_DRAIN(call)                                   \
+  do {                                                           \
+    cudaError_t e_ = (call);                                     \
+    if (e_ != cudaSuccess) return drain(-static_cast<int>(e_));  \
+  } while (0)
   // Host buffers are used in place; they are transferred at full speed only if the caller pinned them
   // (cudaHostRegister / torch pin_memory) - pageable memory still works, through the driver's staging.
   int64_t chunk_i = 0;
@@ -442,13 +470,13 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m, con
     double* din = h->dev_in[slot];
     double* dprior = prior_host ? din + size_t(bn) * m * d : nullptr;
     double* dout = h->dev_out[slot];
-    if (chunk_i >= 2) GPRTO_CUDA(cudaStreamWaitEvent(h->st[0], h->ev_k[slot], 0));    // kernel that read this slot is done
-    GPRTO_CUDA(cudaMemcpyAsync(din, cand_host + size_t(b0) * m * d, size_t(bn) * m * d * sizeof(double), cudaMemcpyHostToDevice, h->st[0]));
+    if (chunk_i >= 2) GPRTO_CUDA_DRAIN(cudaStreamWaitEvent(h->st[0], h->ev_k[slot], 0));    // kernel that read this slot is done
+    GPRTO_CUDA_DRAIN(cudaMemcpyAsync(din, cand_host + size_t(b0) * m * d, size_t(bn) * m * d * sizeof(double), cudaMemcpyHostToDevice, h->st[0]));
     if (prior_host)
-      GPRTO_CUDA(cudaMemcpyAsync(dprior, prior_host + size_t(b0) * m, size_t(bn) * m * sizeof(double), cudaMemcpyHostToDevice, h->st[0]));
-    GPRTO_CUDA(cudaEventRecord(h->ev_h2d[slot], h->st[0]));
-    GPRTO_CUDA(cudaStreamWaitEvent(h->st[1], h->ev_h2d[slot], 0));
-    if (chunk_i >= 2) GPRTO_CUDA(cudaStreamWaitEvent(h->st[1], h->ev_d2h[slot], 0));  // outputs of this slot were copied out
+      GPRTO_CUDA_DRAIN(cudaMemcpyAsync(dprior, prior_host + size_t(b0) * m, size_t(bn) * m * sizeof(double), cudaMemcpyHostToDevice, h->st[0]));
+    GPRTO_CUDA_DRAIN(cudaEventRecord(h->ev_h2d[slot], h->st[0]));
+    GPRTO_CUDA_DRAIN(cudaStreamWaitEvent(h->st[1], h->ev_h2d[slot], 0));
+    if (chunk_i >= 2) GPRTO_CUDA_DRAIN(cudaStreamWaitEvent(h->st[1], h->ev_d2h[slot], 0));  // outputs of this slot were copied out
     double* dmean = nullptr; double* dvar = nullptr; double* dscore = nullptr;
     size_t off = 0;
     if (mean_host) { dmean = dout + off; off += size_t(bn) * m; }
@@ -459,27 +487,28 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m, con
     rc = posterior_device(h, bn, n, d, m, Xn + b0 * n * d, invK + b0 * int64_t(n) * n, alpha + b0 * n, theta_opt + b0 * (d + 2),
                           x_mean + b0 * d, x_std + b0 * d, y_mean + b0, y_std + b0, din, dprior, f_best ? f_best + b0 : nullptr, acq,
                           dmean, dvar, dscore, dbs, dbi, h->st[1]);
-    if (rc) return rc;
-    GPRTO_CUDA(cudaEventRecord(h->ev_k[slot], h->st[1]));
-    GPRTO_CUDA(cudaStreamWaitEvent(h->st[2], h->ev_k[slot], 0));
-    if (mean_host) GPRTO_CUDA(cudaMemcpyAsync(mean_host + size_t(b0) * m, dmean, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
-    if (var_host) GPRTO_CUDA(cudaMemcpyAsync(var_host + size_t(b0) * m, dvar, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
-    if (score_host) GPRTO_CUDA(cudaMemcpyAsync(score_host + size_t(b0) * m, dscore, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
+    if (rc) return drain(rc);
+    GPRTO_CUDA_DRAIN(cudaEventRecord(h->ev_k[slot], h->st[1]));
+    GPRTO_CUDA_DRAIN(cudaStreamWaitEvent(h->st[2], h->ev_k[slot], 0));
+    if (mean_host) GPRTO_CUDA_DRAIN(cudaMemcpyAsync(mean_host + size_t(b0) * m, dmean, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
+    if (var_host) GPRTO_CUDA_DRAIN(cudaMemcpyAsync(var_host + size_t(b0) * m, dvar, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
+    if (score_host) GPRTO_CUDA_DRAIN(cudaMemcpyAsync(score_host + size_t(b0) * m, dscore, size_t(bn) * m * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
     if (best_score_host) {
-      GPRTO_CUDA(cudaMemcpyAsync(best_score_host + b0, dbs, size_t(bn) * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
-      GPRTO_CUDA(cudaMemcpyAsync(best_idx_host + b0, dbi, size_t(bn) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->st[2]));
+      GPRTO_CUDA_DRAIN(cudaMemcpyAsync(best_score_host + b0, dbs, size_t(bn) * sizeof(double), cudaMemcpyDeviceToHost, h->st[2]));
+      GPRTO_CUDA_DRAIN(cudaMemcpyAsync(best_idx_host + b0, dbi, size_t(bn) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->st[2]));
     }
-    GPRTO_CUDA(cudaEventRecord(h->ev_d2h[slot], h->st[2]));
+    GPRTO_CUDA_DRAIN(cudaEventRecord(h->ev_d2h[slot], h->st[2]));
   }
-  GPRTO_CUDA(cudaStreamSynchronize(h->st[2]));
-  GPRTO_CUDA(cudaStreamSynchronize(h->st[1]));
-  GPRTO_CUDA(cudaStreamSynchronize(h->st[0]));
+  GPRTO_CUDA_DRAIN(cudaStreamSynchronize(h->st[2]));
+  GPRTO_CUDA_DRAIN(cudaStreamSynchronize(h->st[1]));
+  GPRTO_CUDA_DRAIN(cudaStreamSynchronize(h->st[0]));
   return 0;
+#undef GPRTO_CUDA_DRAIN
 }
 
 int gprto_sample_candidates(gprto_t* h, int64_t B, int d, int64_t m, const double* centre, const double* radius, int shape,
                             uint64_t seed, const int64_t* idx, double* out, void* stream) {
-  if (!h || B <= 0 || d <= 0 || m <= 0 || !centre || !radius || !out || shape < 0 || shape > 1) return GPRTO_EINVAL;
+  if (!h || B <= 0 || d <= 0 || m <= 0 || !centre || !radius || !out || shape < 0 || shape > 2) return GPRTO_EINVAL;
   DeviceGuard guard(h->device);
   return dispatch_sample(h, B, d, m, centre, radius, shape, seed, idx, out, (cudaStream_t)stream);
 }
@@ -492,7 +521,7 @@ int gprto_posterior_acq_sampled(gprto_t* h, int64_t B, int n, int d, int64_t m, 
   if (!h || B <= 0 || n <= 0 || d <= 0 || m <= 0 || !Xn || !invK || !alpha || !theta_opt || !x_mean || !x_std || !y_mean || !y_std ||
       !centre || !radius || !best_score || !best_idx)
     return GPRTO_EINVAL;
-  if (acq < 1 || acq > 3 || shape < 0 || shape > 1) return GPRTO_EINVAL;
+  if (acq < 1 || acq > 3 || shape < 0 || shape > 2) return GPRTO_EINVAL;
   if (acq == GPRTO_ACQ_EI && !f_best) return GPRTO_EINVAL;
   DeviceGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;

@@ -7,6 +7,19 @@
 #include "../../include/gprto.h"
 
 namespace gprto {
+// One-time per-DEVICE set-up of a kernel (cudaFuncSetAttribute applies to the current device only; a process may hold
+// handles on several devices).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 struct K4Params;
 constexpr int K3R_MAXN = 128;
 constexpr int K3R_MAXD = 8;
@@ -20,4 +33,7 @@ int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const doubl
                    int32_t* status, cudaStream_t s, const int32_t* gidx);
 int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter, double* nll,
                     int32_t* status, cudaStream_t s, const int32_t* gidx);
+// K2 register-tile / DMMA factor kernel (32 < n <= 128; GPRTO_EUNSUPPORTED otherwise)
+int launch_factor_la(int64_t B, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter, double* invK,
+                     double* alpha, double* logdet, int32_t* status, cudaStream_t s);
 }  // namespace gprto

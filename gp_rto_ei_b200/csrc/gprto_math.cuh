@@ -119,6 +119,44 @@ __device__ __forceinline__ void tr_sample(uint64_t seed, int64_t b, int64_t c, i
   }
 }
 
+// Candidate c of GP b as a point: centre + radius * u for the box (shape 0) and ball (shape 1) samplers (rad[0] = the
+// radius).  Shape 2 is the reference's start-point sampler for scaled inputs (ITR_GP_RTO.Ellipse_sampling,
+// sub_uts/utilities_2.py:693-730): u uniform in the unit ball, stretched by the per-dimension semi-axes rad[0..D-1]
+// (the reference's sqrt(0.99) * Delta * sqrt(range_k)), and - as the reference's TR_con test at :725-728 does - accepted
+// only inside the trust-region ball of radius rad[D] (rad[D] <= 0: no ball test).  The reference scans 200 pre-drawn
+// samples for the first accepted one; here attempt a of candidate c is the pure function tr_sample(seed, b, c + a*2^40),
+// up to 64 attempts (the acceptance rate is the area ratio ball / ellipse, 11 % for the Williams-Otto scaling), after
+// which the last sample is pulled radially into the ball.
+template <int D>
+__device__ __forceinline__ void tr_point(uint64_t seed, int64_t b, int64_t c, int shape, const double* __restrict__ centre,
+                                         const double* __restrict__ rad, double (&x)[D]) {
+  double u[D];
+  if (shape != 2) {
+    tr_sample<D>(seed, b, c, shape, u);
+    const double r = rad[0];
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) x[dd] = fma(r, u[dd], centre[dd]);
+    return;
+  }
+  const double ball = rad[D];
+  double off[D];
+  double n2 = 0.0;
+  for (int a = 0; a < 64; ++a) {
+    tr_sample<D>(seed, b, c + (int64_t(a) << 40), 1, u);
+    n2 = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) { off[dd] = rad[dd] * u[dd]; n2 = fma(off[dd], off[dd], n2); }
+    if (!(ball > 0.0) || n2 <= ball * ball) break;
+  }
+  if (ball > 0.0 && n2 > ball * ball) {
+    const double sc = 0.999 * ball * rsqrt(n2);
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) off[dd] *= sc;
+  }
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) x[dd] = centre[dd] + off[dd];
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)

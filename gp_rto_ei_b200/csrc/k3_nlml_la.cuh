@@ -384,15 +384,14 @@ template <int NT, int DT>
 int launch_k3la_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                   double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   const size_t smem = k3la_smem_bytes<NT>(d);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     if (k3la_smem_bytes<NT>(K3R_MAXD) > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            int(k3la_smem_bytes<NT>(K3R_MAXD)));
       if (e != cudaSuccess) return -static_cast<int>(e);
     }
     cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   k3_nlml_la_kernel<NT, DT><<<(unsigned)(B * S), 32 * K3LA<NT>::W, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
   cudaError_t e = cudaGetLastError();
@@ -409,6 +408,7 @@ int launch_k3la(int64_t B, int S, int n, int d, const double* Xn, const double* 
   return launch_k3la_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
+#ifdef GPRTO_K3_TU
 // Look-ahead kernel where it measured faster than k3_nlml_tile_kernel (B200, d = 3, evals/s look-ahead vs plain):
 // n = 48: 4.9e7 vs 4.6e7, n = 64: 3.4e7 vs 3.1e7, n = 80: 1.9e7 vs 2.1e7 (so not used), n = 96: 1.4e7 vs 1.1e7,
 // n = 112: 1.1e7 vs 7.4e6, n = 128: 8.4e6 vs 5.9e6; returns GPRTO_EUNSUPPORTED otherwise (the caller falls back to
@@ -426,5 +426,6 @@ int launch_nlml_la(int64_t B, int S, int n, int d, const double* Xn, const doubl
   }
   return GPRTO_EUNSUPPORTED;
 }
+#endif  // GPRTO_K3_TU
 
 }  // namespace gprto

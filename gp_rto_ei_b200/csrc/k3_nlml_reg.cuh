@@ -251,8 +251,8 @@ template <int NT, int DT>
 int launch_k3r_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                  double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   const size_t smem = k3r_smem_bytes<NT>(d);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     if (k3r_smem_bytes<NT>(K3R_MAXD) > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k3_nlml_tile_kernel<NT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            int(k3r_smem_bytes<NT>(K3R_MAXD)));
@@ -260,7 +260,6 @@ int launch_k3r_d(int64_t B, int S, int n, int d, const double* Xn, const double*
     }
     // without this the driver may size the shared-memory carve-out for a single block of this kernel
     cudaFuncSetAttribute(k3_nlml_tile_kernel<NT, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   k3_nlml_tile_kernel<NT, DT><<<(unsigned)(B * S), 16 * NT, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
   cudaError_t e = cudaGetLastError();
@@ -277,6 +276,7 @@ int launch_k3r(int64_t B, int S, int n, int d, const double* Xn, const double* Y
   return launch_k3r_d<NT, 0>(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
 }
 
+#ifdef GPRTO_K3_TU
 int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                     double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx) {
   if (n > K3R_MAXN || d > K3R_MAXD) return GPRTO_EUNSUPPORTED;
@@ -293,5 +293,6 @@ int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const doub
   }
   return GPRTO_EUNSUPPORTED;
 }
+#endif  // GPRTO_K3_TU
 
 }  // namespace gprto

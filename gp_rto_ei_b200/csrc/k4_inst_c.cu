@@ -7,14 +7,13 @@ namespace {
 template <int NB, int D>
 int launch(const K4Params& p, cudaStream_t s) {
   constexpr size_t smem = k4_smem_bytes<NB, D>();
-  static bool configured = false;   // attributes are per function and idempotent
-  if (!configured) {
+  static PerDeviceOnce once;        // attributes are per function AND per device
+  if (once.first()) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k4_dmma_kernel<NB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e != cudaSuccess) return -static_cast<int>(e);
     }
     cudaFuncSetAttribute(k4_dmma_kernel<NB, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   dim3 grid((unsigned)p.B, p.nchunks);      // GP on x (2^31-1 limit), candidate chunk on y
   k4_dmma_kernel<NB, D><<<grid, K4_THREADS, smem, s>>>(p);

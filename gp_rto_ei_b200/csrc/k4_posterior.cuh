@@ -12,7 +12,7 @@ struct K4Params {
   int64_t chunk;       // candidates per CTA (multiple of 32*warps)
   int nchunks;         // CTAs per GP
   const double *Xn, *invK, *alpha, *theta, *x_mean, *x_std, *y_mean, *y_std, *cand, *prior, *f_best;
-  // fused sampling mode (cand == nullptr): candidate c of GP b = centre[b] + radius[b] * tr_sample(seed, b, c)
+  // fused sampling mode (cand == nullptr): candidate c of GP b = tr_point(seed, b, c, shape, centre[b], radius[b])
   const double *centre, *radius;
   uint64_t seed;
   int shape;
@@ -124,11 +124,10 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (cand[ce * D + dd] - mu_d[dd]) * a_d[dd] : 0.0;
     } else {
-      double u[D];
-      tr_sample<D>(p.seed, b, ce, p.shape, u);
-      const double rad = p.radius[b];
+      double xp[D];
+      tr_point<D>(p.seed, b, ce, p.shape, p.centre + b * D, p.radius + b * (p.shape == 2 ? D + 1 : 1), xp);
 #pragma unroll
-      for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (fma(rad, u[dd], p.centre[b * D + dd]) - mu_d[dd]) * a_d[dd] : 0.0;
+      for (int dd = 0; dd < D; ++dd) xe[dd] = valid ? (xp[dd] - mu_d[dd]) * a_d[dd] : 0.0;
     }
 
     double q_mine = 0.0, m_mine = 0.0;
@@ -299,10 +298,10 @@ __global__ void sample_candidates_kernel(int64_t B, int64_t m, const double* __r
   if (e >= total) return;
   const int64_t b = idx ? e : e / m;
   const int64_t c = idx ? idx[e] : e - b * m;
-  double u[D];
-  tr_sample<D>(seed, b, c, shape, u);
+  double x[D];
+  tr_point<D>(seed, b, c, shape, centre + b * D, radius + b * (shape == 2 ? D + 1 : 1), x);
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) out[e * D + dd] = fma(radius[b], u[dd], centre[b * D + dd]);
+  for (int dd = 0; dd < D; ++dd) out[e * D + dd] = x[dd];
 }
 
 #ifdef GPRTO_API_TU

@@ -54,9 +54,17 @@ const char* gprto_error_string(int code);
  * [3] = max d. */
 int  gprto_limits(int64_t limits[4]);
 int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead;
+                                                                         "k2_path": 0 auto (register-tile / DMMA kernel for 32 < n <= 128), 1 generic (shared memory);
                                                                          "cov_kernel": kernel of gprto_cov_se_ard only: 0 SE-ARD, 1 Matern-3/2, 2 Matern-5/2 */
 /* Number of kernels this library launched through the handle since creation (bench.py's gpu_launches). */
 int64_t gprto_launch_count(const gprto_t* h);
+
+/* Stream ordering of the synchronous *_host entry points.  They run on streams PRIVATE to the handle (created
+ * non-blocking, so they do not synchronise with the legacy default stream); their device-resident inputs (Xn, Yn, invK,
+ * alpha, ...) are usually produced by work the caller enqueued on some other stream.  gprto_order_after(h, s) makes the
+ * NEXT *_host call wait (on the device, cudaStreamWaitEvent) for everything enqueued on stream `s` up to now.  Contract:
+ * either call it with the producing stream before a *_host call, or make sure that stream is idle. */
+int gprto_order_after(gprto_t* h, void* stream);
 
 /* Normalisation of the data set (replaces utilities_2.py:38-40): column mean / population std (ddof = 0).
  * X[B,n,d], Y[B,n] -> x_mean[B,d], x_std[B,d], y_mean[B], y_std[B], Xn[B,n,d], Yn[B,n]. */
@@ -117,8 +125,11 @@ int gprto_posterior_acq(gprto_t* h, int64_t B, int n, int d, int64_t m,
 
 /* Same computation with HOST buffers for the per-candidate streams (cand, prior in; mean, var, score,
  * best_* out); the GP-side arrays (Xn ... y_std, f_best) stay device-resident.  Candidates are processed in
- * GP-chunks through pinned staging buffers on three streams so H2D, compute and D2H overlap; returns
- * after the last copy has completed.  This is the end-to-end entry bench.py times as `e2e`. */
+ * GP-chunks of ~64 MiB, double-buffered in device staging buffers on three streams so H2D, compute and D2H overlap;
+ * the host buffers are read / written IN PLACE (full PCIe speed needs them pinned by the caller - cudaHostRegister or
+ * torch pin_memory -, pageable memory works through the driver's own staging); returns after the last copy has
+ * completed (also on error: copies in flight are drained first).  This is the end-to-end entry bench.py times as `e2e`.
+ * See gprto_order_after for the stream-ordering contract. */
 int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m,
                              const double* Xn, const double* invK, const double* alpha, const double* theta_opt,
                              const double* x_mean, const double* x_std, const double* y_mean, const double* y_std,
@@ -128,7 +139,10 @@ int gprto_posterior_acq_host(gprto_t* h, int64_t B, int n, int d, int64_t m,
 
 /* On-device trust-region candidates (SURVEY.md par. 8f-4; the reference draws its start points on the host,
  * utilities_2.py:678-730).  Candidate c of GP b is a pure function of (seed, b, c):
- *   cand[b,c,:] = centre[b,:] + radius[b] * u,   u uniform in [-1,1]^d (shape 0) or in the unit ball (shape 1).
+ *   cand[b,c,:] = centre[b,:] + radius[b] * u,   u uniform in [-1,1]^d (shape 0) or in the unit ball (shape 1);
+ *   shape 2 = the reference's Ellipse_sampling for scaled inputs (utilities_2.py:693-730): radius is [B, d+1], per-dimension
+ *   semi-axes followed by the trust-region ball radius; u uniform in the unit ball is stretched by the semi-axes and
+ *   re-drawn (up to 64 times) until the point lies inside the ball (radius[b,d] <= 0: no ball test).
  * gprto_sample_candidates materialises them: out[B,m,d], or, with idx[B] != NULL, only candidate idx[b] of each GP
  * (out[B,d]).  gprto_posterior_acq_sampled is K4 with the SAME candidates generated inside the kernel (no candidate
  * array in memory at all); it returns the per-GP arg-min (best_score[B], best_idx[B]) and, if best_x != NULL, the

@@ -179,6 +179,63 @@ def test_k2_factor_matches_reference_inverse(handle, dev):
             assert abs(float(out['logdet'][0]) - logdet) <= 1e-9 * max(1.0, abs(logdet))
 
 
+@pytest.mark.parametrize('n,d,B', [(33, 3, 3), (40, 1, 2), (48, 2, 2), (64, 3, 4), (65, 3, 2), (80, 6, 2), (96, 3, 2), (100, 8, 2), (127, 3, 2),
+                                   (128, 3, 3)])
+def test_k2_register_kernel_matches_lapack_and_generic(handle, dev, n, d, B):
+    """The register-tile / DMMA factor kernel (32 < n <= 128, every tile count, odd n, run-time and compile-time d)
+    against the reference's formula (utilities_2.py:168-175: invKopt = solve(Kopt, I), LU) and against the
+    shared-memory kernel; both Cholesky-based inverses are backward stable: agreement to cond(K)*eps relative to |invK|."""
+    w = workloads.cfg3_numpy(seed=100 + n, B=B, n=n, d=d, m=4)
+    nz = handle.normalise(T(w['X'], dev), T(w['y'], dev))
+    th = T(w['theta'], dev)
+    handle.set_option('k2_path', 0)
+    invK, alpha, logdet, st = handle.factor(nz['Xn'], nz['Yn'], th)
+    handle.set_option('k2_path', 1)
+    invK_g, alpha_g, logdet_g, st_g = handle.factor(nz['Xn'], nz['Yn'], th)
+    handle.set_option('k2_path', 0)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0 and int(st_g.abs().sum()) == 0
+    worst = 0.0
+    for b in range(B):
+        gp = O.make_gp(w['X'][b], w['y'][b], w['theta'][b])
+        cond = np.linalg.cond(gp['invK'])
+        scale = np.abs(gp['invK']).max()
+        A = invK[b].cpu().numpy()
+        assert np.array_equal(A, A.T)
+        err = np.abs(A - gp['invK']).max() / scale
+        worst = max(worst, err / (cond * EPS))
+        assert err <= 50 * cond * EPS, (n, d, b, err, cond)
+        assert np.abs(A - invK_g[b].cpu().numpy()).max() <= 50 * cond * EPS * scale
+        a_ref = gp['invK'] @ gp['y_norm']
+        assert np.abs(alpha[b].cpu().numpy() - a_ref).max() <= 50 * cond * EPS * np.abs(a_ref).max()
+        sign, ld = np.linalg.slogdet(np.linalg.inv(gp['invK']))
+        assert abs(float(logdet[b]) - ld) <= 1e-9 * max(1.0, abs(ld)) and abs(float(logdet_g[b]) - ld) <= 1e-9 * max(1.0, abs(ld))
+        # K invK = I to the conditioning
+        K = np.linalg.inv(gp['invK'])
+        assert np.abs(K @ A - np.eye(n)).max() <= 200 * cond * EPS
+    print('\n[k2 n=%d d=%d] max |invK - LU inverse| / (cond eps |invK|) = %.2f' % (n, d, worst))
+
+
+@pytest.mark.parametrize('n,bad', [(64, 3), (64, 61), (128, 100), (40, 39)])
+def test_k2_register_kernel_reports_failures(handle, dev, n, bad):
+    """A duplicated data point with (numerically) zero noise and no jitter makes the leading minor of order bad+1 singular:
+    dpotrf-style status, NaN outputs, neighbours in the batch unaffected, no hang."""
+    w = workloads.cfg3_numpy(seed=7, B=3, n=n, d=3, m=4)
+    X = w['X'].copy()
+    X[1, bad] = X[1, bad - 1]
+    theta = w['theta'].copy()
+    theta[1, -1] = -400.0
+    nz = handle.normalise(T(X, dev), T(w['y'], dev))
+    for path in (0, 1):
+        handle.set_option('k2_path', path)
+        invK, alpha, logdet, st = handle.factor(nz['Xn'], nz['Yn'], T(theta, dev), jitter=0.0)
+        handle.set_option('k2_path', 0)
+        st = st.cpu().numpy()
+        assert st[0] == 0 and st[2] == 0 and st[1] == bad + 1, (path, st)
+        assert torch.isnan(invK[1]).all() and torch.isnan(alpha[1]).all() and torch.isnan(logdet[1])
+        assert torch.isfinite(invK[0]).all() and torch.isfinite(invK[2]).all()
+
+
 def test_k2_then_k4_device_pipeline_matches_reference(handle, dev):
     """No host in the loop: normalise -> factor -> posterior on the device, against the golden mean/var."""
     g = load_golden('cfg3_small.npz')
@@ -427,7 +484,33 @@ def test_k3_larger_than_register_path_uses_generic(handle, dev):
         assert abs(float(nll[0, s]) - t) <= max(10 * abs(ref - t), 1e-9 * abs(t))
 
 
-@pytest.mark.parametrize('shape', [0, 1])
+def test_ellipse_sampler_follows_the_reference_start_point_rule(handle, dev):
+    """shape 2 = ITR_GP_RTO.Ellipse_sampling with scale_inputs=True (utilities_2.py:693-730): points uniform in the ellipsoid
+    with semi-axes sqrt(0.99) * Delta * sqrt(range_k), accepted only inside the trust-region ball |d| <= Delta."""
+    B, d, m = 3, 2, 20000
+    centre = np.array([[6.9, 83.0], [5.0, 80.0], [4.5, 75.0]])
+    delta = np.array([0.25, 0.7, 0.1])
+    rng_ = np.array([3.0, 30.0])                                  # Williams-Otto input ranges (bounds 4..7, 70..100)
+    rad = np.concatenate([np.sqrt(0.99) * delta[:, None] * np.sqrt(rng_)[None, :], delta[:, None]], axis=1)
+    c = handle.sample_candidates(T(centre, dev), T(rad, dev), m, shape=2, seed=5).cpu().numpy()
+    off = c - centre[:, None, :]
+    r = np.sqrt((off ** 2).sum(-1))
+    assert (r <= delta[:, None] * (1 + 1e-12)).all()                                          # TR_con >= 0 (:726)
+    assert ((off / rad[:, None, :d]) ** 2).sum(-1).max() <= 1 + 1e-6                           # inside the ellipsoid
+    # the accepted points are uniform on ellipse-intersect-ball = the ball here (semi-axes > Delta): mean radius 2/3 Delta
+    assert np.allclose(r.mean(1) / delta, 2.0 / 3.0, atol=0.01)
+    assert np.abs(off.mean(1) / delta[:, None]).max() < 0.02
+    # single candidates by index reproduce the batch; no ball test when radius[d] <= 0 (pure ellipse)
+    idx = torch.tensor([7, 19999, 0], dtype=torch.int64, device=dev)
+    one = handle.sample_candidates(T(centre, dev), T(rad, dev), m, shape=2, seed=5, idx=idx).cpu().numpy()
+    assert np.array_equal(one, c[np.arange(B), [7, 19999, 0]])
+    rad2 = rad.copy(); rad2[:, d] = 0.0
+    c2 = handle.sample_candidates(T(centre, dev), T(rad2, dev), m, shape=2, seed=5).cpu().numpy()
+    q = (((c2 - centre[:, None, :]) / rad2[:, None, :d]) ** 2).sum(-1)
+    assert q.max() <= 1 + 1e-6 and (np.sqrt(((c2 - centre[:, None, :]) ** 2).sum(-1)).max(1) > delta).all()
+
+
+@pytest.mark.parametrize('shape', [0, 1, 2])
 def test_fused_sampling_matches_materialised_candidates(handle, dev, shape):
     """SURVEY.md par. 8f-4: K4 with candidates generated inside the kernel gives bit-identical per-GP results to K4 on the
     same candidates materialised by gprto_sample_candidates; the sampler is uniform in the box / ball and seed-stable."""
@@ -435,6 +518,8 @@ def test_fused_sampling_matches_materialised_candidates(handle, dev, shape):
     gd = handle.fit_fixed(w['X'], w['y'], w['theta'])
     centre = w['X'][:, 5, :].contiguous()
     radius = torch.full((64,), 0.25, dtype=torch.float64, device=dev)
+    if shape == 2:          # semi-axes (0.4, 0.15, 0.3), trust-region ball 0.25
+        radius = torch.tensor([0.4, 0.15, 0.3, 0.25], dtype=torch.float64, device=dev).repeat(64, 1).contiguous()
     m = 5000
     cand = handle.sample_candidates(centre, radius, m, shape=shape, seed=1234)
     again = handle.sample_candidates(centre, radius, m, shape=shape, seed=1234)
@@ -443,6 +528,8 @@ def test_fused_sampling_matches_materialised_candidates(handle, dev, shape):
     u = (cand - centre[:, None, :]) / 0.25
     if shape == 0:
         assert float(u.abs().max()) <= 1.0 and abs(float(u.mean())) < 5e-3 and abs(float(u.var()) - 1.0 / 3.0) < 5e-3
+    elif shape == 2:
+        assert float(u.norm(dim=-1).max()) <= 1.0 + 1e-12 and float((u[..., 1].abs() * 0.25).max()) <= 0.15 + 1e-12
     else:
         r = u.norm(dim=-1)
         assert float(r.max()) <= 1.0 + 1e-6 and abs(float(u.mean())) < 5e-3

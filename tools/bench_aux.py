@@ -28,8 +28,10 @@ def main():
     ap.add_argument('--n', type=int, default=64)
     ap.add_argument('--d', type=int, default=3)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--k2-path', type=int, default=0, help='0 auto (register-tile kernel for 32 < n <= 128), 1 shared-memory kernel')
     a = ap.parse_args()
     h = api.Handle(0)
+    h.set_option('k2_path', a.k2_path)
     w = workloads.cfg3_torch(h.device, seed=0, B=a.B, n=a.n, d=a.d, m=8)
     nz = h.normalise(w['X'], w['y'])
     theta = w['theta']
@@ -43,7 +45,7 @@ def main():
     kbytes = a.B * a.n * a.n * 8.0
     n = a.n
     f_flops = n ** 3 / 3 + n ** 3 / 3 + n ** 3 / 3 + (n * n / 2) * (3 * a.d + 2)      # Cholesky + triangular inverse + L^-T L^-1 + K
-    print(json.dumps({'B': a.B, 'n': a.n, 'd': a.d,
+    print(json.dumps({'B': a.B, 'n': a.n, 'd': a.d, 'k2_path': a.k2_path,
                       'k2_factor': {'ms': ms_f, 'factors_per_s': a.B / (ms_f * 1e-3), 'tflops': a.B * f_flops / (ms_f * 1e-3) / 1e12,
                                     'bytes_out_gbs': (kbytes + a.B * n * 8) / (ms_f * 1e-3) / 1e9},
                       'k1_cov': {'ms': ms_k, 'matrices_per_s': a.B / (ms_k * 1e-3), 'achieved_gbs': kbytes / (ms_k * 1e-3) / 1e9, 'hbm_peak_gbs': hbm,
