@@ -4,11 +4,15 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4]
   (N > 1: launched by torchrun, one rank per GPU)
 
-A step = one pass of the hot path over one batch: for every (GP, candidate) pair the fused kernel K4 produces the
-posterior mean, variance and the EI score plus the per-GP arg-min (and, for N > 1, the NCCL all-gather of the
-per-GP (score, index) records).  Workload = BASELINE.json configs[2] ("synthetic batched GP inference: 65,536
-independent GPs, n=64, d=3, 4,096 EI candidates each"), per GPU (weak scaling: GPs are independent units).
-Prints ONE JSON line (rank 0).
+--workload cfg3 (default, the configuration BASELINE.json's metric is quoted on, configs[2]: "synthetic batched GP inference:
+    65,536 independent GPs, n=64, d=3, 4,096 EI candidates each", per GPU - weak scaling, GPs are independent units).
+    A step = one pass of the hot path over the batch: for every (GP, candidate) pair the fused kernel K4 produces the
+    posterior mean, variance and the EI score plus the per-GP arg-min (and, for N > 1, the NCCL all-gather of the per-GP
+    (score, index) records).
+--workload cfg4 (configs[3]: "batched NLML hyperparameter fit: 16,384 GPs x 64 Sobol multistarts, n=128, d=3, SE-ARD", per
+    GPU).  A step = K3 over all (GP, start) pairs + per-GP arg-min over the starts (utilities_2.py:166) + the gather.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's OWN functions (oracle/ref_cpu_arm.py: the
+unmodified sub_uts/utilities_2.py from the staged baseline/_ref) on the host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -26,6 +30,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+
 def _baseline_metric():
     """The metric name is BASELINE.json's, verbatim."""
     try:
@@ -36,6 +41,7 @@ def _baseline_metric():
 
 
 METRIC = _baseline_metric()
+METRIC_CFG4 = 'NLML evals/sec (FP64, batched Cholesky over Sobol multistarts) at 1/2/4/8 B200; % of roofline'
 UNIT = 'evals/s'
 
 
@@ -67,6 +73,19 @@ def hbm_peak():
             return json.load(fh)['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(summary, kernel_prefix, units):
+    """DRAM bytes per launch from the tracked ncu summary, scaled from the captured slice to `units` of this launch; None if
+    the summary is missing or belongs to another kernel (so that the number cannot silently go stale)."""
+    try:
+        with open(os.path.join(REPO, 'profiles', summary)) as fh:
+            j = json.load(fh)
+        if kernel_prefix not in j['kernel']:
+            return None, None
+        return j['dram_bytes_per_launch'] * units / j['units_in_capture'], summary
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -118,8 +137,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
-def _cpu_worker(args):
-    """Faithful restatement of the reference's per-candidate call structure (oracle, kind='port'), one BLAS thread."""
+def _port_worker_cfg3(args):
+    """Fallback when no copy of the reference is present: the oracle's restatement of the same call structure (kind 'port')."""
     seed, n_gp, n, d, m = args
     from threadpoolctl import threadpool_limits
     from gp_rto_ei_b200 import workloads
@@ -133,95 +152,357 @@ def _cpu_worker(args):
             _, _, s = O.posterior_acq_scalar(w['cand'][b], gps[b], None, w['f_best'][b], 3)
             acc += float(s.min())
         dt = time.perf_counter() - t0
-        t1 = time.perf_counter()
+    return dt, acc
+
+
+def _port_worker_cfg4(args):
+    seed, n_gp, n, d, S = args
+    from threadpoolctl import threadpool_limits
+    from gp_rto_ei_b200 import workloads
+    from oracle import gp_oracle as O
+    with threadpool_limits(1):
+        w = workloads.cfg4_numpy(seed=seed, B=n_gp, n=n, d=d, S=S)
+        nz = [O.normalise(w['X'][b], w['y'][b].reshape(-1, 1)) for b in range(n_gp)]
+        t0 = time.perf_counter()
+        ok = 0
         for b in range(n_gp):
-            O.posterior_acq_vectorised(w['cand'][b], gps[b], None, w['f_best'][b], 3)
-        dtv = time.perf_counter() - t1
-    return dt, dtv, acc
+            v, _ = O.nlml_batch(w['theta'][b], nz[b][4], nz[b][5][:, 0])
+            ok += int((v == v).sum())
+        dt = time.perf_counter() - t0
+    return dt, ok
 
 
-def cpu_baseline_run(n, d, gps_per_core=1, m=2048, cores=None):
-    """Bounded sample of the same workload on all host cores: `cores` processes x gps_per_core GPs x m candidates."""
-    import multiprocessing as mp
+def cpu_baseline_run(workload, n, d, per_core, inner, cores=None, pool=None):
+    """Bounded sample of the same workload on all host cores: `cores` processes x per_core GPs x inner (candidates | starts).
+    The timed code is the reference's own (oracle/ref_cpu_arm.py, kind 'reference') when a copy of the reference is present."""
+    from oracle import ref_cpu_arm as R
     cores = cores or len(os.sched_getaffinity(0))
-    ctx = mp.get_context('spawn')
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, gps_per_core, n, d, m) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    evals = cores * gps_per_core * m
-    t_scalar = max(r[0] for r in res)
-    t_vec = max(r[1] for r in res)
-    return {'value': evals / t_scalar, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d processes x %d GP x %d candidates (n=%d, d=%d), oracle/gp_oracle.posterior_acq_scalar = the reference\'s '
-                      'one-candidate-at-a-time GP_obj_f -> GP_inference_np call structure, 1 BLAS thread per process' % (cores, gps_per_core, m, n, d),
-            'per_core': evals / t_scalar / cores, 'vectorised_numpy_value': evals / t_vec, 'pool_wall_s': wall}
+    use_ref = R.available()
+    if workload == 'cfg3':
+        worker = R.cfg3_worker if use_ref else _port_worker_cfg3
+        what = ('ITR_GP_RTO.GP_obj_f -> GP_model.GP_inference_np of the UNMODIFIED reference (sub_uts/utilities_2.py:477-507, 235-278), one '
+                'candidate per call' if use_ref else 'oracle/gp_oracle.posterior_acq_scalar (restatement of GP_obj_f -> GP_inference_np)')
+        unit_name = 'candidates'
+    else:
+        worker = R.cfg4_worker if use_ref else _port_worker_cfg4
+        what = ('GP_model.negative_loglikelihood of the UNMODIFIED reference (sub_uts/utilities_2.py:92-114), one hyper-parameter vector per '
+                'call' if use_ref else 'oracle/gp_oracle.nlml (restatement of negative_loglikelihood)')
+        unit_name = 'Sobol starts'
+    res, wall = R.run_pool(worker, [(1000 + i, per_core, n, d, inner) for i in range(cores)], cores, pool)
+    evals = cores * per_core * inner
+    t = max(r[0] for r in res)
+    return {'value': evals / t, 'unit': UNIT, 'cores': cores, 'kind': 'reference' if use_ref else 'port',
+            'sample': '%d processes x %d GP x %d %s (n=%d, d=%d), %s, 1 BLAS thread per process' % (cores, per_core, inner, unit_name, n, d, what),
+            'per_core': evals / t / cores, 'pool_wall_s': wall, 'reference_root': os.path.relpath(R.ref_harness.REFERENCE_ROOT, REPO)
+            if use_ref and R.ref_harness.REFERENCE_ROOT.startswith(REPO) else (R.ref_harness.REFERENCE_ROOT if use_ref else None)}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    n, d, m = 64, 3, 4096
+    cfg4 = args.workload == 'cfg4'
+    n, d = (128, 3) if cfg4 else (64, 3)
+    inner = 64 if cfg4 else 4096
+    per_core = 2 if cfg4 else 1
     vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_baseline_run(n, d, gps_per_core=1, m=4096)
-        if i >= args.warmup:
-            vals.append(r)
+    from oracle import ref_cpu_arm as R
+    with R.make_pool() as pool:                 # one pool of worker processes for all steps (imports paid once, in the warm-up)
+        for i in range(args.warmup + args.steps):
+            r = cpu_baseline_run(args.workload, n, d, per_core, inner, pool=pool)
+            if i >= args.warmup:
+                vals.append(r)
     v = sum(x['value'] for x in vals) / len(vals)
-    evals_per_step = vals[0]['cores'] * 4096
-    line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3 * evals_per_step / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': {'workload': 'cfg3: synthetic batched GP inference, 65,536 GPs x 4,096 EI candidates, n=64, d=3 '
-                                            '(bounded sample per step, see cpu_baseline.sample)'},
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': vals[0]['cores'], 'kind': 'port', 'sample': vals[0]['sample'],
-                             'vectorised_numpy_value': sum(x['vectorised_numpy_value'] for x in vals) / len(vals)},
+    evals_per_step = vals[0]['cores'] * per_core * inner
+    desc = ('cfg4 (BASELINE.json configs[3]): batched NLML hyper-parameter fit, 16,384 GPs x 64 Sobol multistarts, n=128, d=3' if cfg4 else
+            'cfg3 (BASELINE.json configs[2]): synthetic batched GP inference, 65,536 GPs x 4,096 EI candidates, n=64, d=3')
+    line = {'metric': METRIC_CFG4 if cfg4 else METRIC, 'value': v, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * evals_per_step / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': desc + ' (bounded sample per step, see cpu_baseline.sample)'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': vals[0]['cores'], 'kind': vals[0]['kind'], 'sample': vals[0]['sample'],
+                             'reference_root': vals[0]['reference_root']},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
 
 
-def nlml_secondary(h, dev, B=2048, S=64, n=128, d=3, reps=3):
-    """Secondary metric (BASELINE.json configs[3], cfg 4): batched NLML evaluations / s, K3, on a 1/8 slice of the
-    16,384 x 64 sweep (the rate is size-independent: one CTA per (GP, start), 131,072 CTAs here)."""
+# ------------------------------------------------------------------------------------------ helpers of the GPU arm
+class Ctx:
+    pass
+
+
+def make_ctx(args):
+    import torch
+    from gp_rto_ei_b200 import api, parallel
+    c = Ctx()
+    c.rank, c.local_rank, c.world = parallel.init()
+    if c.world != args.gpus and c.rank == 0:
+        print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, c.world), file=sys.stderr)
+    torch.cuda.set_device(c.local_rank)
+    c.dev = torch.device('cuda', c.local_rank)
+    c.h = api.Handle(c.local_rank)
+    return c
+
+
+def sync_all(c):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if c.world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(c, x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def sum_over_ranks(c, x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0])
+
+
+def timed_steps(c, step, warmup, steps):
+    """W untimed steps, then exactly K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max
+    over ranks.  Returns (ms_total over ranks, per-step device ms on this rank, launches)."""
+    import torch
+    for _ in range(warmup):
+        step()
+    sync_all(c)
+    launches0 = c.h.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sync_all(c)
+    e0.record()
+    for i in range(steps):
+        evk[i][0].record()
+        step()
+        evk[i][1].record()
+    e1.record()
+    sync_all(c)
+    launches = c.h.launch_count - launches0
+    ms_total = max_over_ranks(c, e0.elapsed_time(e1))
+    k_ms = sum(a.elapsed_time(b) for a, b in evk) / steps
+    return ms_total, k_ms, launches
+
+
+def pcie_peak(c, nbytes=1 << 30):
+    """Pinned-memory copy bandwidth of this box, each direction alone and both at once (two streams) - the e2e legs'
+    own roofline.  GB/s per direction."""
+    import torch
+    hb_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    hb_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=c.dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=c.dev)
+    s1, s2 = torch.cuda.Stream(device=c.dev), torch.cuda.Stream(device=c.dev)
+
+    def run(h2d, d2h, reps=3):
+        best = 1e30
+        for _ in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(hb_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    hb_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return nbytes / best / 1e9
+    out = {'h2d_alone_gbs': run(True, False), 'd2h_alone_gbs': run(False, True), 'bidirectional_each_way_gbs': run(True, True),
+           'how': 'torch pinned <-> device copies of 1 GiB, best of 3, wall clock around synchronize'}
+    del hb_in, hb_out, d_in, d_out
+    return out
+
+
+def host_mem_ok(c, need_bytes):
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 2.5 * need_bytes * c.world + (8 << 30)
+    except Exception:
+        return False
+
+
+# ------------------------------------------------------------------------------------------ cfg 4 (NLML sweep)
+def cfg4_setup(c, B, S, n, d, seed):
     import torch
     from gp_rto_ei_b200 import workloads
-    w = workloads.cfg4_torch(dev, seed=1, B=B, n=n, d=d, S=S)
-    nz = h.normalise(w['X'], w['y'])
-    nll = torch.empty(B, S, dtype=torch.float64, device=dev)
-    st = torch.empty(B, S, dtype=torch.int32, device=dev)
-    h.nlml(nz['Xn'], nz['Yn'], w['theta'], out=nll, status=st)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        h.nlml(nz['Xn'], nz['Yn'], w['theta'], out=nll, status=st)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    peak, _ = fp64_peak()
+    w = workloads.cfg4_torch(c.dev, seed=seed, B=B, n=n, d=d, S=S)
+    nz = c.h.normalise(w['X'], w['y'])
+    st = dict(w=w, nz=nz, nll=torch.empty(B, S, dtype=torch.float64, device=c.dev), status=torch.empty(B, S, dtype=torch.int32, device=c.dev),
+              best_v=torch.empty(B, dtype=torch.float64, device=c.dev), best_i=torch.empty(B, dtype=torch.int64, device=c.dev),
+              rec=torch.empty(B, 2, dtype=torch.float64, device=c.dev))
+    return st
+
+
+def cfg4_step(c, st, B, S, n, d, lo):
+    """K3 over all (GP, start) pairs, per-GP arg-min over the starts (utilities_2.py:166), and the gather of (nll_best, idx)."""
+    from gp_rto_ei_b200 import api, parallel
+    lib, hp, P, h = c.h.lib, c.h._h, api._ptr, c.h
+    nz, w = st['nz'], st['w']
+    api._lib.check(lib.gprto_nlml(hp, B, S, n, d, P(nz['Xn']), P(nz['Yn']), P(w['theta']), 1e-8, P(st['nll']), P(st['status']), h._stream()), 'gprto_nlml')
+    api._lib.check(lib.gprto_argmin(hp, B, S, P(st['nll']), P(st['best_v']), P(st['best_i']), h._stream()), 'gprto_argmin')
+    if c.world > 1:
+        api._lib.check(lib.gprto_pack_best(hp, B, P(st['best_v']), P(st['best_i']), 0, P(st['rec']), h._stream()), 'gprto_pack_best')
+        return parallel.allgather_records(st['rec'])
+    return None
+
+
+def nlml_block(c, B, S, n, d, steps, warmup, label, with_e2e=True):
+    """Timed cfg-4 block (used as the headline of --workload cfg4 and as `secondary` of cfg3): dict with value / roofline / e2e."""
+    import torch
+    st = cfg4_setup(c, B, S, n, d, seed=1 + 1000 * c.rank)
+    ms_total, k_ms, launches = timed_steps(c, lambda: cfg4_step(c, st, B, S, n, d, 0), warmup, steps)
+    ms = ms_total / steps
+    evals = float(B) * S * c.world
+    peak, peak_src = fp64_peak()
     F = flops_nlml(n, d)
-    tf = B * S * F / (ms * 1e-3) / 1e12
-    return {'metric': 'NLML evals/s (FP64, batched), cfg 4 slice: %d GPs x %d Sobol starts, n=%d, d=%d' % (B, S, n, d),
-            'value': B * S / (ms * 1e-3), 'unit': 'evals/s', 'ms_per_sweep': ms, 'flops_per_eval': F,
-            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'kernel': 'k3_nlml_tile_kernel<16,3>'},
-            'failed_factorisations': int((st != 0).sum())}
+    tf = float(B) * S * F / (k_ms * 1e-3) / 1e12
+    failed = sum_over_ranks(c, float((st['status'] != 0).sum()))
+    out = {'metric': METRIC_CFG4, 'workload': label, 'value': evals / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'n_gpus': c.world,
+           'gps_per_gpu': B, 'starts': S, 'n': n, 'd': d, 'flops_per_eval': F, 'gpu_launches': launches,
+           'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'kernel': 'k3_nlml_la_kernel<%d,%d>' % ((n + 15) // 16 * 2, d),
+                        'kernel_ms': k_ms, 'peak_source': 'FP64 ' + peak_src},
+           'failed_factorisations': int(failed),
+           'note_failures': 'corners of the reference hyper-parameter box (sn2 = e^-16, sf2 = e^10) are indefinite in FP64; the reference would raise there (utilities_2.py:107)'}
+    tr, src = ncu_traffic('k3_ncu_summary.json', 'k3_nlml_la_kernel', float(B) * S)
+    out['roofline']['traffic'] = tr
+    out['roofline']['traffic_source'] = src
+    if with_e2e:
+        # e2e: theta from pinned host memory every step, (nll_best, idx) per GP back to pinned host memory
+        th_h = st['w']['theta'].cpu().pin_memory()
+        bv_h = torch.empty(B, dtype=torch.float64).pin_memory()
+        bi_h = torch.empty(B, dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            st['w']['theta'].copy_(th_h, non_blocking=True)
+            cfg4_step(c, st, B, S, n, d, 0)
+            bv_h.copy_(st['best_v'], non_blocking=True)
+            bi_h.copy_(st['best_i'], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        sync_all(c)
+        k = max(2, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        out['e2e'] = {'value': evals * k / dt, 'unit': UNIT, 'h2d_bytes_per_step': B * S * (d + 2) * 8, 'd2h_bytes_per_step': B * 16,
+                      'sample': 'theta[%d,%d,%d] H2D from pinned memory, gprto_nlml + gprto_argmin, (nll_best, idx) D2H, %d steps' % (B, S, d + 2, k)}
+    return out
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def run_cfg4(args, c):
+    B, S, n, d = args.B4, args.S, args.n4, args.d
+    sampler = ClockSampler(c.local_rank)
+    if c.rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    blk = nlml_block(c, B, S, n, d, args.steps, args.warmup, 'cfg4')
+    clocks = sampler.stop() if c.rank == 0 else None
+    if c.rank != 0:
+        return
+    cpu = None if args.skip_extras else cpu_baseline_run('cfg4', n, d, 2, S)
+    # parity sample: 4 GPs x all starts against the oracle (the reference raises where the oracle reports failure)
+    from oracle import gp_oracle as O
     import numpy as np
+    st = cfg4_setup(c, 4, S, n, d, seed=1 + 1000 * c.rank)
+    cfg4_step(c, st, 4, S, n, d, 0)
+    nll = st['nll'].cpu().numpy(); stat = st['status'].cpu().numpy()
+    Xh, yh, th = st['w']['X'].cpu().numpy(), st['w']['y'].cpu().numpy(), st['w']['theta'].cpu().numpy()
+    worst, mism = 0.0, 0
+    for b in range(4):
+        _, _, _, _, Xn, Yn = O.normalise(Xh[b], yh[b].reshape(-1, 1))
+        ref, rst = O.nlml_batch(th[b], Xn, Yn[:, 0])
+        ok = (rst == 0) & (stat[b] == 0)
+        mism += int(((rst == 0) != (stat[b] == 0)).sum())
+        worst = max(worst, float(np.max(np.abs(nll[b][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok])))))
+    line = {'metric': blk['metric'], 'value': blk['value'], 'unit': UNIT, 'n_gpus': c.world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': blk['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'cfg4 (BASELINE.json configs[3]): batched NLML hyper-parameter fit, %d GPs per GPU x %d Sobol multistarts, n=%d, d=%d, '
+                                   'SE-ARD; per step: K3 sweep + per-GP arg-min over the starts%s' % (B, S, n, d, ' + NCCL all-gather of (nll_best, idx)' if c.world > 1 else ''),
+                       'gps_per_gpu': B, 'starts': S, 'n': n, 'd': d, 'parallelism': 'gp-sharded x%d' % c.world,
+                       'l2': 'inputs are 4 KB per GP and stay L2-resident; the kernel is FP64-compute bound (no HBM stream to flush)'},
+            'e2e': blk['e2e'], 'gpu_launches': blk['gpu_launches'], 'clocks': clocks, 'roofline': blk['roofline'], 'cpu_baseline': cpu,
+            'failed_factorisations': blk['failed_factorisations'],
+            'parity': {'sample': '4 GPs x %d starts vs oracle.nlml (restatement of negative_loglikelihood, pinned bit-for-bit to the reference)' % S,
+                       'max_rel_err_where_both_succeed': worst, 'failure_flag_mismatches': mism,
+                       'note': 'near the indefinite corners cond(K) ~ 1e16 and two correct algorithms differ by cond*eps (tests arbitrate with long double)'}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ cfg 3 (posterior + EI)
+def parity_block(c, w, gd, mean, var, score, best_i, cand, f_best, npar, n_truth, d, m):
+    """Parity of the GPU results on a sample of the bench batch, reported four ways per quantity (SURVEY.md par. 7.3-2):
+    pointwise max relative error vs the oracle, error normalised by the natural scale of the quantity, the sample's
+    max cond(K), and GPU-vs-long-double-truth beside oracle-vs-long-double-truth (which of the two is closer to the exact value)."""
+    import numpy as np
+    from scipy.stats import norm as _norm
+    from oracle import gp_oracle as O
+    Xh, yh, th = w['X'][:npar].cpu().numpy(), w['y'][:npar].cpu().numpy(), w['theta'][:npar].cpu().numpy()
+    ch, fh = cand[:npar].cpu().numpy(), f_best[:npar].cpu().numpy()
+    mg, vg, sg = mean[:npar].cpu().numpy(), var[:npar].cpu().numpy(), score[:npar].cpu().numpy()
+    pw = {'mean': 0.0, 'var': 0.0, 'score': 0.0}
+    sc = {'mean': 0.0, 'var': 0.0, 'score': 0.0}
+    truth = {'gpu_mean': 0.0, 'oracle_mean': 0.0, 'gpu_var': 0.0, 'oracle_var': 0.0}
+    conds, mismatch, compared = [], 0, 0
+    tiny = 1e-300
+    for b in range(npar):
+        gp = O.make_gp(Xh[b], yh[b], th[b])
+        conds.append(float(np.linalg.cond(gp['invK'])))
+        mv, vv, sv = O.posterior_acq_vectorised(ch[b], gp, None, fh[b], 3)
+        sf2 = math.exp(2 * th[b][d])
+        sig = np.sqrt(vv); dl = fh[b] - mv
+        with np.errstate(divide='ignore', invalid='ignore'):
+            z = np.where(sig == 0, 0.0, dl / sig)
+        ei_scale = float(np.max(sig * _norm.pdf(z) + np.abs(dl) * _norm.cdf(z)))
+        pw['mean'] = max(pw['mean'], float(np.max(np.abs(mg[b] - mv) / np.maximum(np.abs(mv), tiny))))
+        pw['var'] = max(pw['var'], float(np.max(np.abs(vg[b] - vv) / np.maximum(np.abs(vv), tiny))))
+        pw['score'] = max(pw['score'], float(np.max(np.abs(sg[b] - sv) / np.maximum(np.abs(sv), tiny))))
+        sc['mean'] = max(sc['mean'], float(np.max(np.abs(mg[b] - mv)) / np.max(np.abs(mv))))
+        sc['var'] = max(sc['var'], float(np.max(np.abs(vg[b] - vv)) / (sf2 * gp['Y_std'] ** 2)))
+        sc['score'] = max(sc['score'], float(np.max(np.abs(sg[b] - sv)) / max(ei_scale, tiny)))
+        srt = np.sort(sv)
+        if srt[1] - srt[0] > 1e-9 * ei_scale:                       # selected candidate: compared where the gap exceeds the tolerance
+            compared += 1
+            mismatch += int(int(best_i[b]) != int(np.argmin(sv)))
+        if b < n_truth:
+            xn = (ch[b] - gp['X_mean']) / gp['X_std']
+            tr = O.truth_ld(gp['X_norm'], gp['y_norm'], th[b], xn)
+            m_true = tr['mean_norm'] * gp['Y_std'] + gp['Y_mean']
+            v_true = tr['var_norm'] * gp['Y_std'] ** 2
+            ms_, vs_ = float(np.max(np.abs(m_true))), sf2 * gp['Y_std'] ** 2
+            truth['gpu_mean'] = max(truth['gpu_mean'], float(np.max(np.abs(mg[b] - m_true))) / ms_)
+            truth['oracle_mean'] = max(truth['oracle_mean'], float(np.max(np.abs(mv - m_true))) / ms_)
+            truth['gpu_var'] = max(truth['gpu_var'], float(np.max(np.abs(vg[b] - v_true))) / vs_)
+            truth['oracle_var'] = max(truth['oracle_var'], float(np.max(np.abs(vv - v_true))) / vs_)
+    return {'sample': '%d GPs x %d candidates of the bench batch vs oracle (vectorised NumPy restatement of GP_inference_np + GP_obj_f)' % (npar, m),
+            'pointwise_max_rel_err': pw,
+            'pointwise_note': 'pointwise relative error is dominated by candidates where the quantity itself cancels (mean crossing zero, EI -> 0 '
+                              'in the tail, var -> 0 next to data): |err| / |value| with |value| << scale',
+            'scale_normalised_max_err': sc,
+            'scale_note': 'mean by max|mean| of the GP, var by the prior variance sf2*y_std^2, score by max(sigma*phi + |Delta|*Phi)',
+            'max_cond_K': max(conds), 'median_cond_K': sorted(conds)[len(conds) // 2],
+            'vs_long_double_truth': dict(truth, sample='%d GPs; 80-bit Cholesky-form evaluation of the same formulas (oracle.truth_ld); scale-normalised' % n_truth),
+            'argmin_compared': compared, 'argmin_mismatch': mismatch,
+            'tolerance': 'north_star 1e-9 relative: met scale-normalised; pointwise it is met wherever |value| > cond(K)*eps*scale '
+                         '(tests/test_gpu_parity.py asserts |gpu-ref| <= 1e-9|ref| + first-order rounding floor of the reference formula)'}
+
+
+def run_cfg3(args, c):
     import torch
     import torch.distributed as dist
     from gp_rto_ei_b200 import api, parallel, workloads
-
-    rank, local_rank, world = parallel.init()
-    if world != args.gpus:
-        if rank == 0:
-            print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    h = api.Handle(local_rank)
-
+    rank, world, dev, h = c.rank, c.world, c.dev, c.h
     n, d = args.n, args.d
     B, m = args.B, args.m
     w = workloads.cfg3_torch(dev, seed=1000 * rank, B=B, n=n, d=d, m=m)
@@ -233,7 +514,6 @@ def run_ours(args):
     best_s = torch.empty(B, dtype=torch.float64, device=dev); best_i = torch.empty(B, dtype=torch.int64, device=dev)
     rec = torch.empty(B, 2, dtype=torch.float64, device=dev)
     lib, hp, P = h.lib, h._h, api._ptr
-    lo, _ = parallel.shard_range(B * world, rank, world)
 
     def step():
         api._lib.check(lib.gprto_posterior_acq(hp, B, n, d, m, P(gd['Xn']), P(gd['invK']), P(gd['alpha']), P(gd['theta']), P(gd['x_mean']),
@@ -244,49 +524,26 @@ def run_ours(args):
             return parallel.allgather_records(rec)
         return None
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(c.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)                     # let nvidia-smi come up; its first samples are idle ones
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    launches0 = h.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        evk[i][0].record()
-        step()
-        evk[i][1].record()
-    e1.record()
-    sync_all()
-    launches = h.launch_count - launches0
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t[0])
+    ms_total, k4_ms, launches = timed_steps(c, step, args.warmup, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     evals_step = float(B) * m * world
     value = evals_step / (ms_step * 1e-3)
-    k4_ms = sum(a.elapsed_time(b) for a, b in evk) / args.steps      # per-step device time on this rank (K4 dominates)
 
     if args.skip_extras:
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'ms_per_step': ms_step, 'kernel_ms': k4_ms, 'gpu_launches': launches}))
         return
 
-    # ---- e2e: host buffers through the C-ABI host entry (H2D of candidates, D2H of mean/var/score/best inside the timed region)
-    Be = min(B, args.e2e_B)
+    # ---- e2e: host buffers through the C-ABI host entry (H2D of candidates, D2H of mean/var/score/best inside the timed region),
+    # on the FULL batch when the host has the memory for the pinned buffers (12.9 GB per rank), else on a quarter of it
+    need = B * m * (d + 3) * 8
+    Be = B if (args.e2e_B <= 0 and host_mem_ok(c, need)) else min(B, args.e2e_B if args.e2e_B > 0 else B // 4)
+    pcie = pcie_peak(c)
     cand_h = torch.empty(Be, m, d, dtype=torch.float64).pin_memory()
     cand_h.copy_(cand[:Be])
     outs = dict(mean=torch.empty(Be, m, dtype=torch.float64).pin_memory(), var=torch.empty(Be, m, dtype=torch.float64).pin_memory(),
@@ -294,34 +551,24 @@ def run_ours(args):
                 best_idx=torch.empty(Be, dtype=torch.int64).pin_memory())
     gsub = {k: v[:Be] for k, v in gd.items()}
     fb = f_best[:Be]
-    for _ in range(2):
-        h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs)
-    sync_all()
-    t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs)       # returns after the last D2H completed
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = float(Be) * m * world * e2e_steps / float(t[0])
+
+    def e2e_run(out_dict):
+        h.posterior_acq_host(gsub, cand_h, None, fb, 3, out_dict)
+        sync_all(c)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h.posterior_acq_host(gsub, cand_h, None, fb, 3, out_dict)       # returns after the last D2H completed
+        torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        return float(Be) * m * world * e2e_steps / dt, dt / e2e_steps
+    e2e_value, e2e_s = e2e_run(outs)
     assert torch.equal(outs['score'][:4], score[:4].cpu())
     h2d = Be * m * d * 8
     d2h = Be * m * 3 * 8 + Be * 16
     # variant that returns only what the RTO loop consumes (per-GP best score + index): same H2D, 16 B per GP back
-    outs_b = {k: outs[k] for k in ('best_score', 'best_idx')}
-    h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs_b)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        h.posterior_acq_host(gsub, cand_h, None, fb, 3, outs_b)
-    torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_best_value = float(Be) * m * world * e2e_steps / float(t[0])
+    e2e_best_value, e2e_best_s = e2e_run({k: outs[k] for k in ('best_score', 'best_idx')})
+    del cand_h, outs
     # variant with on-device candidates (gprto_posterior_acq_sampled): per GP only (centre, radius) go in (H2D from pinned
     # memory each step) and (best score, best index, best point) come back; full batch of B GPs
     ctr_h = w['X'][:, 0, :].contiguous().cpu().pin_memory()
@@ -338,65 +585,34 @@ def run_ours(args):
             so_h[k].copy_(so[k], non_blocking=True)
         torch.cuda.synchronize()
     sampled_step(0)
-    sync_all()
+    sync_all(c)
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         sampled_step(i + 1)
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sampled_value = float(B) * m * world * e2e_steps / float(t[0])
+    e2e_sampled_value = float(B) * m * world * e2e_steps / max_over_ranks(c, time.perf_counter() - t0)
+
+    # ---- secondary metric on every N: cfg-4 NLML sweep, 1/8 of the per-GPU batch (the rate is size-independent: one CTA per (GP, start))
+    nlml = None
+    if not args.no_nlml:
+        try:
+            nlml = nlml_block(c, 2048, 64, 128, d, 3, 1, 'cfg4 slice (1/8 of the 16,384 x 64 sweep per GPU)', with_e2e=False)
+        except Exception as exc:          # secondary line must never take the headline down
+            nlml = {'error': repr(exc)}
 
     if rank != 0:
         if world > 1:
             dist.barrier()
         return
 
-    # ---- parity sample against the oracle (outside the timed region)
-    from oracle import gp_oracle as O
-    npar = 64
-    # errors are normalised by the natural scale of each quantity over the GP's candidate set (a pointwise relative error is
-    # meaningless where the mean crosses zero or where EI has cancelled to ~0): mean by max|mean|, variance by the prior
-    # variance sf2*y_std^2, score by max(sigma*phi + |Delta|*Phi)
-    from scipy.stats import norm as _norm
-    worst = {'mean': 0.0, 'var': 0.0, 'score': 0.0, 'argmin_mismatch': 0}
-    Xh, yh, th = w['X'][:npar].cpu().numpy(), w['y'][:npar].cpu().numpy(), w['theta'][:npar].cpu().numpy()
-    ch, fh = cand[:npar].cpu().numpy(), f_best[:npar].cpu().numpy()
-    for b in range(npar):
-        gp = O.make_gp(Xh[b], yh[b], th[b])
-        mv, vv, sv = O.posterior_acq_vectorised(ch[b], gp, None, fh[b], 3)
-        sf2 = math.exp(2 * th[b][d])
-        sig = np.sqrt(vv); dl = fh[b] - mv
-        with np.errstate(divide='ignore', invalid='ignore'):
-            z = np.where(sig == 0, 0.0, dl / sig)
-        ei_scale = float(np.max(sig * _norm.pdf(z) + np.abs(dl) * _norm.cdf(z)))
-        worst['mean'] = max(worst['mean'], float(np.max(np.abs(mean[b].cpu().numpy() - mv)) / np.max(np.abs(mv))))
-        worst['var'] = max(worst['var'], float(np.max(np.abs(var[b].cpu().numpy() - vv)) / (sf2 * gp['Y_std'] ** 2)))
-        worst['score'] = max(worst['score'], float(np.max(np.abs(score[b].cpu().numpy() - sv)) / max(ei_scale, 1e-300)))
-        srt = np.sort(sv)
-        if srt[1] - srt[0] > 1e-9 * ei_scale:                       # selected candidate: compared where the gap exceeds the tolerance
-            worst['argmin_mismatch'] += int(int(best_i[b]) != int(np.argmin(sv)))
-
-    nlml = None
-    if world == 1 and not args.no_nlml:
-        try:
-            nlml = nlml_secondary(h, dev)
-        except Exception as exc:          # secondary line must never take the headline down
-            nlml = {'error': repr(exc)}
-    cpu = cpu_baseline_run(n, d, gps_per_core=2, m=4096)      # ~12 s of CPU work on 16 cores
+    parity = parity_block(c, w, gd, mean, var, score, best_i, cand, f_best, 64, 8, d, m)
+    cpu = cpu_baseline_run('cfg3', n, d, 4, 4096)      # ~20-30 s of CPU work in total
     peak, peak_src = fp64_peak()
     F = flops_eval(n, d)
     achieved = (float(B) * m * F) / (k4_ms * 1e-3) / 1e12
     hbm, hbm_src = hbm_peak()
     alg_bytes = 8.0 * (d + 3) + 8.0 * (n * n + n * d + n + 3 * d + 4) / m
-    traffic = None
-    try:
-        with open(os.path.join(REPO, 'profiles', 'k4_ncu_summary.json')) as fh_:
-            j_ = json.load(fh_)
-            # ncu capture was taken on a slice of the batch (same kernel, same per-GP work): scale to this launch
-            traffic = j_['dram_bytes_per_launch'] * (float(B) * m) / (j_['gps_in_capture'] * j_['candidates_per_gp'])
-    except Exception:
-        pass
+    traffic, traffic_src = ncu_traffic('k4_ncu_summary.json', 'k4_dmma_kernel', float(B) * m)
+    bidir = pcie['bidirectional_each_way_gbs']
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -407,23 +623,31 @@ def run_ours(args):
                          (B * m * d * 8 / 1e9, B * n * n * 8 / 1e9),
                    'collective': 'NCCL all-gather of per-GP (score, idx) records each step' if world > 1 else 'none (single GPU)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'sample': 'gprto_posterior_acq_host on %d GPs x %d candidates per GPU, pinned host buffers, %d steps' % (Be, m, e2e_steps),
+                'sample': 'gprto_posterior_acq_host on %d of %d GPs x %d candidates per GPU (%s), pinned host buffers, %d steps' %
+                          (Be, B, m, 'full config' if Be == B else 'host memory bounded', e2e_steps),
+                'pcie_gbs_each_way': {'h2d': h2d / e2e_s / 1e9, 'd2h': d2h / e2e_s / 1e9},
+                'pcie_peak': pcie, 'pcie_frac': max(h2d, d2h) / e2e_s / 1e9 / bidir,
+                'bound': 'PCIe: 24 B in + 24 B out per evaluation; pcie_frac = achieved GB/s of the busier direction / measured bidirectional pinned-copy peak',
                 'best_only': {'value': e2e_best_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': Be * 16,
-                              'note': 'same call returning only the per-GP arg-min (what the RTO loop consumes)'},
+                              'pcie_frac': h2d / e2e_best_s / 1e9 / pcie['h2d_alone_gbs'],
+                              'note': 'same call returning only the per-GP arg-min - what the RTO loop consumes (utilities_2.py:991); '
+                                      'this is the variant the drop-in ITR_GP_RTO uses for host-generated SLSQP iterates'},
                 'sampled_on_device': {'value': e2e_sampled_value, 'unit': UNIT, 'h2d_bytes_per_step': B * (d + 1) * 8, 'd2h_bytes_per_step': B * (d + 2) * 8,
                                       'note': 'gprto_posterior_acq_sampled: the %d trust-region (ball) candidates of each of %d GPs are generated inside K4 from '
-                                              '(centre, radius, seed); returns best score / index / point per GP' % (m, B)}},
+                                              '(centre, radius, seed) - the device form of the multistart seeding of utilities_2.py:970-975; returns best score / '
+                                              'index / point per GP; not PCIe-bound' % (m, B)}},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'kernel': 'k4_dmma_kernel<8,3>', 'kernel_ms': k4_ms, 'flops_per_eval': F, 'peak_source': 'FP64 ' + peak_src +
-                     '; FP64 DMMA and DFMA share one pipe on B200, MEASURED_PEAKS.json has no FP64 entry',
+                     'traffic_source': traffic_src, 'kernel': 'k4_dmma_kernel<8,3>', 'kernel_ms': k4_ms, 'flops_per_eval': F,
+                     'executed_note': 'algorithmic flops (the reference\'s dense quadratic form); the kernel folds invK into a triangular matrix and executes '
+                                      '72 of 128 DMMA fragments per tile, so the executed pipe utilisation is the ncu figure (DMMA 47.7 % + FP64 38.6 % = 86 %)',
+                     'peak_source': 'FP64 ' + peak_src + '; FP64 DMMA and DFMA share one pipe on B200, MEASURED_PEAKS.json has no FP64 entry',
                      'hbm_check': {'algorithmic_bytes_per_eval': alg_bytes, 'achieved_gbs': float(B) * m * alg_bytes / (k4_ms * 1e-3) / 1e9,
                                    'peak_gbs': hbm, 'peak_source': hbm_src}},
         'cpu_baseline': cpu,
         'secondary': nlml,
-        'parity': {'sample': '%d GPs x %d candidates vs oracle (vectorised NumPy restatement); errors relative to max|mean|, prior '
-                             'variance and the EI magnitude of each GP' % (npar, m), 'max_rel_err': worst},
+        'parity': parity,
     }
     print(json.dumps(line))
     if world > 1:
@@ -436,11 +660,15 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--B', type=int, default=65536)
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg4'])
+    ap.add_argument('--B', type=int, default=65536, help='cfg3: GPs per GPU')
     ap.add_argument('--m', type=int, default=4096)
     ap.add_argument('--n', type=int, default=64)
     ap.add_argument('--d', type=int, default=3)
-    ap.add_argument('--e2e-B', dest='e2e_B', type=int, default=16384)
+    ap.add_argument('--B4', type=int, default=16384, help='cfg4: GPs per GPU')
+    ap.add_argument('--S', type=int, default=64)
+    ap.add_argument('--n4', type=int, default=128)
+    ap.add_argument('--e2e-B', dest='e2e_B', type=int, default=0, help='GPs of the e2e leg (0: the full batch if host memory allows, else a quarter)')
     ap.add_argument('--no-nlml', action='store_true')
     ap.add_argument('--skip-extras', action='store_true', help='profiling runs: no e2e / CPU baseline / parity legs')
     args = ap.parse_args()
@@ -449,7 +677,11 @@ def main():
     if args.impl == 'reference':
         run_reference(args)
     else:
-        run_ours(args)
+        c = make_ctx(args)
+        if args.workload == 'cfg4':
+            run_cfg4(args, c)
+        else:
+            run_cfg3(args, c)
     try:
         import torch.distributed as dist
         if dist.is_initialized():

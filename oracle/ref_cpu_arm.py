@@ -116,10 +116,18 @@ def cfg4_worker(args):
     return dt, ok
 
 
-def run_pool(worker, jobs, cores=None):
+def make_pool(cores=None):
     import multiprocessing as mp
     cores = cores or len(os.sched_getaffinity(0))
+    return mp.get_context('spawn').Pool(cores)
+
+
+def run_pool(worker, jobs, cores=None, pool=None):
+    """Map `jobs` over `cores` worker processes (one job each); a caller-owned pool is reused across steps."""
     t0 = time.perf_counter()
-    with mp.get_context('spawn').Pool(cores) as pool:
-        res = pool.map(worker, jobs)
+    if pool is not None:
+        res = pool.map(worker, jobs, chunksize=1)
+    else:
+        with make_pool(cores) as p:
+            res = p.map(worker, jobs, chunksize=1)
     return res, time.perf_counter() - t0

@@ -218,20 +218,28 @@ def test_k2_register_kernel_matches_lapack_and_generic(handle, dev, n, d, B):
 
 @pytest.mark.parametrize('n,bad', [(64, 3), (64, 61), (128, 100), (40, 39)])
 def test_k2_register_kernel_reports_failures(handle, dev, n, bad):
-    """A duplicated data point with (numerically) zero noise and no jitter makes the leading minor of order bad+1 singular:
-    dpotrf-style status, NaN outputs, neighbours in the batch unaffected, no hang."""
+    """A duplicated data point with zero noise and a slightly NEGATIVE diagonal shift makes a leading minor at or before
+    row bad+1 robustly indefinite (an exactly singular one can come out as a tiny positive pivot): dpotrf-style status
+    equal to LAPACK's info on the oracle's matrix, NaN outputs, neighbours in the batch unaffected, no hang."""
+    from scipy.linalg import lapack
     w = workloads.cfg3_numpy(seed=7, B=3, n=n, d=3, m=4)
     X = w['X'].copy()
     X[1, bad] = X[1, bad - 1]
     theta = w['theta'].copy()
     theta[1, -1] = -400.0
     nz = handle.normalise(T(X, dev), T(w['y'], dev))
+    _, _, _, _, Xn1, _ = O.normalise(X[1], w['y'][1].reshape(-1, 1))
+    W, sf2, sn2 = O.unpack_theta(theta[1], 3)
+    info = lapack.dpotrf(O.cov_mat('RBF', Xn1, W, sf2) + (sn2 - 1e-3) * np.eye(n), lower=1)[1]
+    assert 0 < info <= bad + 1
+    # the healthy neighbours carry noise >= 1e-3 + margin so that the same shift leaves them positive definite
+    theta[0, -1] = theta[2, -1] = 0.5 * np.log(1e-2)
     for path in (0, 1):
         handle.set_option('k2_path', path)
-        invK, alpha, logdet, st = handle.factor(nz['Xn'], nz['Yn'], T(theta, dev), jitter=0.0)
+        invK, alpha, logdet, st = handle.factor(nz['Xn'], nz['Yn'], T(theta, dev), jitter=-1e-3)
         handle.set_option('k2_path', 0)
         st = st.cpu().numpy()
-        assert st[0] == 0 and st[2] == 0 and st[1] == bad + 1, (path, st)
+        assert st[0] == 0 and st[2] == 0 and st[1] == info, (path, st, info)
         assert torch.isnan(invK[1]).all() and torch.isnan(alpha[1]).all() and torch.isnan(logdet[1])
         assert torch.isfinite(invK[0]).all() and torch.isfinite(invK[2]).all()
 
