@@ -419,13 +419,21 @@ def run_cfg4(args, c):
     cfg4_step(c, st, 4, S, n, d, 0)
     nll = st['nll'].cpu().numpy(); stat = st['status'].cpu().numpy()
     Xh, yh, th = st['w']['X'].cpu().numpy(), st['w']['y'].cpu().numpy(), st['w']['theta'].cpu().numpy()
-    worst, mism = 0.0, 0
+    worst, mism, worst_cond_ok = 0.0, 0, 0.0
+    gpu_t, ora_t = 0.0, 0.0
     for b in range(4):
         _, _, _, _, Xn, Yn = O.normalise(Xh[b], yh[b].reshape(-1, 1))
         ref, rst = O.nlml_batch(th[b], Xn, Yn[:, 0])
         ok = (rst == 0) & (stat[b] == 0)
         mism += int(((rst == 0) != (stat[b] == 0)).sum())
-        worst = max(worst, float(np.max(np.abs(nll[b][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok])))))
+        rel = np.abs(nll[b] - ref) / np.maximum(1.0, np.abs(ref))
+        worst = max(worst, float(np.max(rel[ok])))
+        if b < 2:                               # 80-bit arbiter on every start of two GPs: which side is closer to the exact value
+            for s_ in np.flatnonzero(ok):
+                tv = O.truth_ld(Xn, Yn[:, 0], th[b][s_], jitter=1e-8)['nll']
+                if np.isfinite(tv):
+                    gpu_t = max(gpu_t, abs(nll[b][s_] - tv) / max(1.0, abs(tv)))
+                    ora_t = max(ora_t, abs(ref[s_] - tv) / max(1.0, abs(tv)))
     line = {'metric': blk['metric'], 'value': blk['value'], 'unit': UNIT, 'n_gpus': c.world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': blk['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'cfg4 (BASELINE.json configs[3]): batched NLML hyper-parameter fit, %d GPs per GPU x %d Sobol multistarts, n=%d, d=%d, '
@@ -436,7 +444,9 @@ def run_cfg4(args, c):
             'failed_factorisations': blk['failed_factorisations'],
             'parity': {'sample': '4 GPs x %d starts vs oracle.nlml (restatement of negative_loglikelihood, pinned bit-for-bit to the reference)' % S,
                        'max_rel_err_where_both_succeed': worst, 'failure_flag_mismatches': mism,
-                       'note': 'near the indefinite corners cond(K) ~ 1e16 and two correct algorithms differ by cond*eps (tests arbitrate with long double)'}}
+                       'vs_long_double_truth': {'gpu': gpu_t, 'oracle': ora_t, 'sample': '2 GPs x every start both sides factorise; 80-bit Cholesky (oracle.truth_ld)'},
+                       'note': 'the Sobol box reaches sn2 = e^-16, sf2 = e^10: cond(K) up to ~1e16 there, where two correct algorithms differ by cond*eps; '
+                               'the long-double arbiter shows which side carries the error'}}
     print(json.dumps(line))
 
 
