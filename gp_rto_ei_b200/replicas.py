@@ -49,8 +49,9 @@ def problem_setup(name):
     raise ValueError(name)
 
 
-def run_replica(seed, problem='simple', obj_setting=3, n_iter=20, multi_opt=30, multi_hyper=15):
-    """One seeded episode; returns the noise-free objective of the final iterate, its feasibility and the iterate."""
+def run_replica(seed, problem='simple', obj_setting=3, n_iter=20, multi_opt=30, multi_hyper=15, trajectory=False):
+    """One seeded episode through the sequential drop-in (ITR_GP_RTO.RTO_routine); returns the noise-free objective of the
+    final iterate, its feasibility and the iterate (trajectory=True: also X_opt, y_opt, TR_l, backtrack)."""
     from gp_rto_ei_b200.sub_uts import utilities_2 as u2
     p = problem_setup(problem)
     np.random.seed(seed)
@@ -64,7 +65,10 @@ def run_replica(seed, problem='simple', obj_setting=3, n_iter=20, multi_opt=30, 
     x = np.asarray(xnew, dtype=float).flatten()
     f = float(np.asarray(p['truth'](x)).reshape(-1)[0])
     feas = all(float(np.asarray(c(x)).reshape(-1)[0]) > 0 for c in p['truth_cons'])
-    return dict(seed=seed, objective=f, feasible=bool(feas), x=x.tolist(), backtracks=int(np.sum(backtrack)), TR_final=float(TR_l[-1]))
+    out = dict(seed=seed, objective=f, feasible=bool(feas), x=x.tolist(), backtracks=int(np.sum(backtrack)), TR_final=float(TR_l[-1]))
+    if trajectory:
+        out.update(X_opt=np.asarray(X_opt), y_opt=np.asarray(y_opt), TR_l=np.asarray(TR_l, dtype=float), backtrack=np.asarray(backtrack, dtype=bool))
+    return out
 
 
 def _worker(args):

@@ -58,114 +58,125 @@ def fd_steps(x0, lb, ub, eps=_EPS):
     return h
 
 
-class _Inst:
-    __slots__ = ('idx', 'x', 'state', 'fx', 'g', 'C', 'd', 'mult', 'buffer', 'indices', 'nfev', 'njev', 'done')
+def _check_scipy():
+    """This module drives a PRIVATE SciPy routine with the state-dict calling convention introduced in SciPy 1.16 and sizes
+    its workspace with SciPy's own formula; tests/test_slsqp_batch.py (mandatory CPU test) pins bit-identity with
+    scipy.optimize.minimize for the installed version.  Refuse versions older than the C port."""
+    import scipy
+    major, minor = (int(v) for v in scipy.__version__.split('.')[:2])
+    if (major, minor) < (1, 16):
+        raise ImportError('slsqp_batch needs SciPy >= 1.16 (state-dict _slsqplib.slsqp); found ' + scipy.__version__)
 
 
-def minimize_batch(fun_batch, x0s, bounds, con_batch=None, m_ineq=0, ftol=1e-6, maxiter=100, eps=_EPS, inst_ids=None):
-    """Run len(x0s) SLSQP instances in lock step.  bounds: (n, 2) array shared by all instances or a list of such
-    arrays (one per instance).  Returns a list of Result(x, fun, nit, nfev, njev, status, message, success)."""
-    x0s = [np.asarray(x, dtype=float).reshape(-1) for x in x0s]
-    K = len(x0s)
-    n = x0s[0].size
-    if isinstance(bounds, np.ndarray) and bounds.ndim == 2:
-        bounds = [bounds] * K
+_check_scipy()
+
+
+def minimize_arrays(fun_batch, X0, LB, UB, con_batch=None, m_ineq=0, ftol=1e-6, maxiter=100, eps=_EPS, inst_ids=None):
+    """Core of the lock-step driver, struct-of-arrays: K instances of dimension n (X0, LB, UB: [K, n]) advanced together.
+    All per-round bookkeeping (clipping, forward-difference points, gradients, constraint normals) is one NumPy
+    operation over the instances of the round; the only per-instance Python work is the call of SciPy's C routine.
+    Returns dict(x[K,n], fun[K], status[K], nit[K], nfev[K], njev[K], jac[K,n], mult[K,m])."""
+    X0 = np.asarray(X0, dtype=float)
+    K, n = X0.shape
+    LB = np.ascontiguousarray(np.broadcast_to(np.asarray(LB, dtype=float), (K, n)))
+    UB = np.ascontiguousarray(np.broadcast_to(np.asarray(UB, dtype=float), (K, n)))
+    if (LB > UB).any():
+        raise ValueError('SLSQP Error: lb > ub in bounds')
     m = int(m_ineq) if con_batch is not None else 0
-    insts = []
-    lbs, ubs, xls, xus = [], [], [], []
+    m1 = max(1, m)
+    ids = np.arange(K) if inst_ids is None else np.asarray(inst_ids)
+    XL, XU = LB.copy(), UB.copy()
+    XL[~np.isfinite(LB)] = np.nan
+    XU[~np.isfinite(UB)] = np.nan
+    X = np.clip(X0, LB, UB)
+    FX = np.zeros(K)
+    G = np.zeros((K, n))
+    CT = np.zeros((K, n, m1))                 # CT[k].T is the (m, n) Fortran-ordered constraint-normal matrix of instance k
+    D = np.zeros((K, m1))
+    MULT = np.zeros((K, max(1, m + 2 * n + 2)))
+    size = n * (n + 1) // 2 + 3 * m * n + 9 * m + 8 * n * n + 35 * n + 28
+    if m == 0:
+        size += 2 * n * (n + 1)
+    BUF = np.zeros((K, max(size, 1)))
+    IND = np.zeros((K, max(m + 2 * n + 2, 1)), dtype=np.int64 if _ILP64 else np.int32)
+    NFEV = np.zeros(K, dtype=np.int64)
+    NJEV = np.zeros(K, dtype=np.int64)
+    states, args = [], []
     for k in range(K):
-        b = np.asarray(bounds[k], dtype=float)
-        lb, ub = b[:, 0].copy(), b[:, 1].copy()
-        if (lb > ub).any():
-            raise ValueError('SLSQP Error: lb > ub in bounds')
-        xl, xu = lb.copy(), ub.copy()
-        xl[~np.isfinite(lb)] = np.nan
-        xu[~np.isfinite(ub)] = np.nan
-        lbs.append(lb); ubs.append(ub); xls.append(xl); xus.append(xu)
-        it = _Inst()
-        it.idx = k if inst_ids is None else inst_ids[k]
-        it.x = np.clip(x0s[k], lb, ub)
-        it.state = {'acc': ftol, 'alpha': 0.0, 'f0': 0.0, 'gs': 0.0, 'h1': 0.0, 'h2': 0.0, 'h3': 0.0, 'h4': 0.0, 't': 0.0,
-                    't0': 0.0, 'tol': 10.0 * ftol, 'exact': 0, 'inconsistent': 0, 'reset': 0, 'iter': 0, 'itermax': int(maxiter),
-                    'line': 0, 'm': m, 'meq': 0, 'mode': 0, 'n': n}
-        it.indices = np.zeros([max(m + 2 * n + 2, 1)], dtype=np.int64 if _ILP64 else np.int32)
-        size = n * (n + 1) // 2 + 3 * m * n + 9 * m + 8 * n * n + 35 * n + 28
-        if m == 0:
-            size += 2 * n * (n + 1)
-        it.buffer = np.zeros(max(size, 1), dtype=np.float64)
-        it.mult = np.zeros([max(1, m + 2 * n + 2)], dtype=np.float64)
-        it.C = np.zeros([max(1, m), n], dtype=np.float64, order='F')
-        it.d = np.zeros([max(1, m)], dtype=np.float64)
-        it.g = np.zeros(n)
-        it.fx = 0.0
-        it.nfev = it.njev = 0
-        it.done = False
-        insts.append(it)
-
-    LB, UB = np.asarray(lbs), np.asarray(ubs)
+        st = {'acc': ftol, 'alpha': 0.0, 'f0': 0.0, 'gs': 0.0, 'h1': 0.0, 'h2': 0.0, 'h3': 0.0, 'h4': 0.0, 't': 0.0,
+              't0': 0.0, 'tol': 10.0 * ftol, 'exact': 0, 'inconsistent': 0, 'reset': 0, 'iter': 0, 'itermax': int(maxiter),
+              'line': 0, 'm': m, 'meq': 0, 'mode': 0, 'n': n}
+        states.append(st)
+        args.append((G[k], CT[k].T, D[k], X[k], MULT[k], XL[k], XU[k], BUF[k], IND[k]))
     eye = np.eye(n)
 
     def evaluate(need_f, need_g):
-        """One batched round: f (and c) at the iterates of need_f, forward differences for need_g.  All index and
-        step arithmetic is vectorised over the instances of the round (one NumPy call each, not one per instance)."""
-        need_f, need_g = list(need_f), list(need_g)
-        nf, ng_ = len(need_f), len(need_g)
+        """One batched round: f (and c) at the iterates of need_f, forward differences for need_g (index arrays)."""
+        nf, ng_ = need_f.size, need_g.size
         if nf + ng_ == 0:
             return
-        blocks, ids = [], []
+        blocks, pid = [], []
         if nf:
-            Xf = np.clip(np.stack([insts[k].x for k in need_f]), LB[need_f], UB[need_f])
-            blocks.append(Xf)
-            ids.extend(insts[k].idx for k in need_f)
+            blocks.append(np.clip(X[need_f], LB[need_f], UB[need_f]))
+            pid.append(ids[need_f])
         if ng_:
-            Xg = np.clip(np.stack([insts[k].x for k in need_g]), LB[need_g], UB[need_g])
+            Xg = np.clip(X[need_g], LB[need_g], UB[need_g])
             H = fd_steps(Xg, LB[need_g], UB[need_g], eps)                      # [ng, n]
             # point (k, i) = x_k + h_ki e_i ; the step actually taken is (x + h) - x  (approx_derivative does the same)
             Pg = Xg[:, None, :] + H[:, :, None] * eye[None, :, :]            # [ng, n, n]
             DX = (Xg + H) - Xg
             blocks.append(Pg.reshape(ng_ * n, n))
-            for k in need_g:
-                ids.extend([insts[k].idx] * n)
-        ids = np.asarray(ids)
+            pid.append(np.repeat(ids[need_g], n))
         P = np.concatenate(blocks, axis=0)
-        f = np.asarray(fun_batch(ids, P), dtype=float).reshape(-1)
-        c = np.asarray(con_batch(ids, P), dtype=float).reshape(P.shape[0], m) if m else None
-        for j, k in enumerate(need_f):
-            it = insts[k]
-            it.fx = float(f[j]); it.nfev += 1
+        pid = np.concatenate(pid)
+        f = np.asarray(fun_batch(pid, P), dtype=float).reshape(-1)
+        c = np.asarray(con_batch(pid, P), dtype=float).reshape(P.shape[0], m) if m else None
+        if nf:
+            FX[need_f] = f[:nf]
+            NFEV[need_f] += 1
             if m:
-                it.d[:m] = c[j]
+                D[need_f, :m] = c[:nf]
         if ng_:
-            Fg = f[nf:].reshape(ng_, n)
-            Cg = c[nf:].reshape(ng_, n, m) if m else None
-            for j, k in enumerate(need_g):
-                it = insts[k]
-                it.g[:] = (Fg[j] - it.fx) / DX[j]
-                if m:
-                    # c(x0) is the value stored at the last f/c evaluation of the same point (deterministic: not re-evaluated)
-                    it.C[:m, :] = ((Cg[j] - it.d[:m][None, :]) / DX[j][:, None]).T
-                it.nfev += n; it.njev += 1
+            G[need_g] = (f[nf:].reshape(ng_, n) - FX[need_g][:, None]) / DX
+            if m:
+                # c(x0) is the value stored at the last f/c evaluation of the same point (deterministic: not re-evaluated)
+                CT[need_g, :, :m] = (c[nf:].reshape(ng_, n, m) - D[need_g, None, :m]) / DX[:, :, None]
+            NFEV[need_g] += n
+            NJEV[need_g] += 1
 
     # mode 0 on entry: objective, constraints and both gradients at x0
-    evaluate(range(K), range(K))
-    active = list(range(K))
-    while active:
-        need_f, need_g, still = [], [], []
-        for k in active:
-            it = insts[k]
-            _slsqp(it.state, it.fx, it.g, it.C, it.d, it.x, it.mult, xls[k], xus[k], it.buffer, it.indices)
-            mode = it.state['mode']
-            if mode == 1:
-                need_f.append(k); still.append(k)
-            elif mode == -1:
-                need_g.append(k); still.append(k)
-            else:
-                it.done = True
-        evaluate(need_f, need_g)
-        active = still
+    allk = np.arange(K)
+    evaluate(allk, allk)
+    active = allk
+    while active.size:
+        fxl = FX[active].tolist()
+        modes = np.empty(active.size, dtype=np.int64)
+        for j, k in enumerate(active.tolist()):
+            st = states[k]
+            _slsqp(st, fxl[j], *args[k])
+            modes[j] = st['mode']
+        evaluate(active[modes == 1], active[modes == -1])
+        active = active[np.abs(modes) == 1]
+    status = np.array([st['mode'] for st in states], dtype=np.int64)
+    nit = np.array([st['iter'] for st in states], dtype=np.int64)
+    return dict(x=X, fun=FX, status=status, nit=nit, nfev=NFEV, njev=NJEV, jac=G, mult=MULT[:, :m])
+
+
+def minimize_batch(fun_batch, x0s, bounds, con_batch=None, m_ineq=0, ftol=1e-6, maxiter=100, eps=_EPS, inst_ids=None):
+    """Run len(x0s) SLSQP instances in lock step.  bounds: (n, 2) array shared by all instances or a list of such
+    arrays (one per instance).  Returns a list of Result(x, fun, nit, nfev, njev, status, message, success)."""
+    X0 = np.stack([np.asarray(x, dtype=float).reshape(-1) for x in x0s])
+    K = X0.shape[0]
+    if isinstance(bounds, np.ndarray) and bounds.ndim == 2:
+        B = np.broadcast_to(bounds[None], (K,) + bounds.shape)
+    else:
+        B = np.stack([np.asarray(b, dtype=float) for b in bounds])
+    r = minimize_arrays(fun_batch, X0, B[:, :, 0], B[:, :, 1], con_batch=con_batch, m_ineq=m_ineq, ftol=ftol, maxiter=maxiter, eps=eps,
+                        inst_ids=inst_ids)
     out = []
-    for it in insts:
-        mode = it.state['mode']
-        out.append(Result(x=it.x, fun=it.fx, jac=it.g, nit=it.state['iter'], nfev=it.nfev, njev=it.njev, status=mode,
-                          message=EXIT_MODES.get(mode, 'unknown'), success=(mode == 0), multipliers=it.mult[:m]))
+    for k in range(K):
+        mode = int(r['status'][k])
+        out.append(Result(x=r['x'][k], fun=float(r['fun'][k]), jac=r['jac'][k], nit=int(r['nit'][k]), nfev=int(r['nfev'][k]),
+                          njev=int(r['njev'][k]), status=mode, message=EXIT_MODES.get(mode, 'unknown'), success=(mode == 0),
+                          multipliers=r['mult'][k]))
     return out

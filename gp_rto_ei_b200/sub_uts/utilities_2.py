@@ -241,6 +241,33 @@ def Second_diff_fxx(f, x):
     return H
 
 
+# -------------------------------------------------------------------------------------------- start-point samplers (:678-730)
+def ball_sample(np_rng, py_rng, ndim, Delta0):
+    """ITR_GP_RTO.Ball_sampling (utilities_2.py:678-687) on explicit generators: np_rng = numpy.random (module, global
+    state) or a numpy.random.RandomState; py_rng = the stdlib random module or a random.Random - the reference draws the
+    direction from NumPy's generator and the radius from the stdlib one (:682-684), in this order."""
+    u = np_rng.normal(0, 1, ndim)
+    length = np.sum(u ** 2) ** 0.5
+    r = py_rng.random() ** (1.0 / ndim)
+    return r * u / length * Delta0 * 2
+
+
+def ellipse_sample(np_rng, ndim, TRmat, Delta0):
+    """ITR_GP_RTO.Ellipse_sampling (utilities_2.py:693-730): 200 points uniform in the ellipsoid S = inv(TRmat) Delta0^2
+    (shrunk by sqrt(0.99)), the first one inside the trust-region ball |d| <= Delta0 (TR_con >= 0, :726) is returned."""
+    m_fa = 200
+    S = np.linalg.inv(TRmat) * Delta0 ** 2
+    pts = np_rng.normal(size=(ndim, m_fa))
+    pts = pts / np.sqrt(np.sum(np.square(pts), axis=0))[None, :]
+    radii = np.power(np_rng.rand(1, m_fa), 1.0 / ndim)
+    ell = np.linalg.cholesky(S).T @ (radii * pts) * np.sqrt(0.99)
+    for i in range(m_fa):
+        d = ell[:, i].reshape(1, -1)
+        if Delta0 ** 2 - d @ d.T >= 0:
+            return np.array(ell[:, i]).flatten()
+    raise RuntimeError('no trust-region start point found among %d samples' % m_fa)   # the reference would NameError
+
+
 # -------------------------------------------------------------------------------------------- RTO driver (:338-1038)
 class ITR_GP_RTO:
     """Trust-region GP real-time optimisation.  Constructor signature, attributes used by the scripts and the
@@ -358,22 +385,10 @@ class ITR_GP_RTO:
 
     # ---- start points (utilities_2.py:678-730); RNG calls in the reference's order
     def Ball_sampling(self, ndim):
-        u = np.random.normal(0, 1, ndim)
-        length = np.sum(u ** 2) ** 0.5
-        r = random.random() ** (1.0 / ndim)
-        return r * u / length * self.Delta0 * 2
+        return ball_sample(np.random, random, ndim, self.Delta0)
 
     def Ellipse_sampling(self, ndim):
-        m_fa = 200
-        S = np.linalg.inv(self.TRmat) * self.Delta0 ** 2
-        pts = np.random.normal(size=(ndim, m_fa))
-        pts = pts / np.sqrt(np.sum(np.square(pts), axis=0))[None, :]
-        radii = np.power(np.random.rand(1, m_fa), 1.0 / ndim)
-        ell = np.linalg.cholesky(S).T @ (radii * pts) * np.sqrt(0.99)
-        for i in range(m_fa):
-            if self.TR_con(ell[:, i].reshape(1, -1)) >= 0:
-                return np.array(ell[:, i]).flatten()
-        raise RuntimeError('no trust-region start point found among %d samples' % m_fa)   # the reference would NameError
+        return ellipse_sample(np.random, ndim, self.TRmat, self.Delta0)
 
     # ---- GP construction (utilities_2.py:783-831): objective + ng constraint GPs, fitted together in lock step
     def GPs_construction(self, xk, Xtrain, ytrain, ndatplus, H_norm=0.):
@@ -407,13 +422,22 @@ class ITR_GP_RTO:
         con_gp = {k: v[1:].contiguous() for k, v in group.items()} if ng else None
         cache = {}
 
+        from . import systems as _systems
+        model_batch = _systems.batch_form([self.obj_model] + list(self.cons_model))     # None unless all are known callables
+
         def evaluate(P):
             Xq = P + xk.reshape(1, ndim)
-            prior = np.array([[float(self.obj_model(x)) for x in Xq]])
+            if model_batch is not None:
+                # same arithmetic per point as the scalar callables (bit-identical, see systems.py), all points at once
+                M = model_batch(Xq)
+                prior, cprior = np.ascontiguousarray(M[:, 0][None]), np.ascontiguousarray(M[:, 1:].T)
+            else:
+                prior = np.array([[float(self.obj_model(x)) for x in Xq]])
             sc = h.posterior_acq_host_np(obj_gp, Xq[None], prior, fb, self.obj, want=('score',))['score'][0]
             cons = np.empty((P.shape[0], ng + 1))
             if ng:
-                cprior = np.array([[float(np.asarray(self.cons_model[g](x)).reshape(-1)[0]) for x in Xq] for g in range(ng)])
+                if model_batch is None:
+                    cprior = np.array([[float(np.asarray(self.cons_model[g](x)).reshape(-1)[0]) for x in Xq] for g in range(ng)])
                 cm = h.posterior_acq_host_np(con_gp, np.broadcast_to(Xq, (ng,) + Xq.shape), cprior, None, api.ACQ_MEAN,
                                              want=('score',))['score']
                 cons[:, :ng] = cm.T
