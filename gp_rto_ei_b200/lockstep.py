@@ -133,7 +133,7 @@ class LockstepRTO:
             return out
 
         res = slsqp_batch.minimize_arrays(fun_batch, x0, lb, ub, ftol=1e-12, maxiter=10000)
-        self.stats['slsqp_calls_fit'] += int(res['nit'].sum())
+        self.stats['slsqp_calls_fit'] += res['slsqp_calls']
         vals = res['fun'].reshape(R * G, S_)
         best = np.argmin(vals, axis=1)                                       # first minimum wins (utilities_2.py:166)
         theta = res['x'].reshape(R * G, S_, d + 2)[np.arange(R * G), best]
@@ -203,7 +203,7 @@ class LockstepRTO:
 
         res = slsqp_batch.minimize_arrays(fun_batch, d_inits.reshape(-1, d), lb, ub, con_batch=con_batch, m_ineq=ng + 1, ftol=1e-12,
                                           maxiter=10000)
-        self.stats['slsqp_calls_acq'] += int(res['nit'].sum())
+        self.stats['slsqp_calls_acq'] += res['slsqp_calls']
         return res
 
     # ---------------------------------------------------------------- the episode (utilities_2.py:888-1038)

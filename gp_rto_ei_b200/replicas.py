@@ -4,14 +4,19 @@ sharded over the GPUs of one box, gathered with one NCCL all-gather of (objectiv
 The reference runs its 30 "Monte-Carlo" episodes sequentially in one Python process sharing one RNG stream
 (run_simple/main_simple.py:174, run_WO/main_WO_prior_EI.py:105).  Here replica r is an independent unit seeded with
 ``np.random.seed(r); random.seed(r)`` (both RNGs: the reference leaves the stdlib one unseeded, utilities_2.py:684), so
-any replica can be reproduced on its own.  Rank k of K owns replicas [lo, hi) = parallel.shard_range(R, k, K) and runs
-them one after the other (an episode is host-bound - SciPy's SLSQP state machine runs in Python - at 0.87 s for the toy
-problem against ~26 s for the reference).  `--workers W` fans a rank's shard out over W processes sharing its GPU; without
-MPS the processes time-slice the device and this measured SLOWER (128 toy replicas on 4 GPUs: 49.6 s with 4 workers per
-GPU vs ~30 s expected with 1), so the default is 1.  The only collective is the final gather.
+any replica can be reproduced on its own.  Rank k of K owns replicas [lo, hi) = parallel.shard_range(R, k, K).
+
+--mode lockstep (default): the rank's replicas advance TOGETHER (gp_rto_ei_b200/lockstep.py): every SLSQP round of every
+replica's fit / acquisition is one batched kernel launch, the host only runs SciPy's SLSQP C routine per instance.  A
+lock-step replica is bit-identical to the same seed run on its own (tests/test_gpu_lockstep.py).  `--workers W` splits the
+rank's block over W processes sharing its GPU, each in lock step on its part: the per-instance SLSQP calls (~6 us each,
+GIL-bound) are the bottleneck, so W = host cores / GPUs scales almost linearly; the kernels of W processes time-slice the
+device, which is idle most of the time anyway.
+--mode sequential: one episode after the other through the drop-in's ITR_GP_RTO (0.87 s per toy episode; reference ~26 s).
+The only collective is the final gather of (objective, replica id).
 
     python -m torch.distributed.run --nproc-per-node 8 -m gp_rto_ei_b200.replicas --replicas 8192 --problem wo --workers 4
-    python -m gp_rto_ei_b200.replicas --replicas 16 --problem simple            (single GPU)
+    python -m gp_rto_ei_b200.replicas --replicas 64 --problem simple            (single GPU)
 """
 import argparse
 import contextlib
@@ -78,16 +83,83 @@ def _worker(args):
     return [run_replica(s, **kw) for s in seeds]
 
 
-def run_shard(seeds, device, workers, kw):
+def _lockstep_worker(args):
+    """One process: its seeds in lock step (gp_rto_ei_b200/lockstep.py), in batches of at most `batch` replicas."""
+    seeds, device, kw, batch = args
+    import torch
+    torch.cuda.set_device(device)
+    from gp_rto_ei_b200 import api, lockstep
+    h = api.default_handle(device)
+    out, stats = [], {}
+    t0 = time.perf_counter()
+    for lo in range(0, len(seeds), batch):
+        chunk = list(seeds[lo:lo + batch])
+        ls = lockstep.LockstepRTO(kw['problem'], chunk, obj_setting=kw['obj_setting'], n_iter=kw['n_iter'], multi_opt=kw['multi_opt'],
+                                  multi_hyper=kw['multi_hyper'], handle=h)
+        res = ls.run()
+        f, feas = ls.outcome(res)
+        for j, sd in enumerate(chunk):
+            out.append(dict(seed=sd, objective=float(f[j]), feasible=bool(feas[j]), x=res['xnew'][j].tolist(),
+                            backtracks=int(res['backtrack'][j].sum()), TR_final=float(res['TR_l'][j, -1]), dead=bool(res['dead'][j])))
+        for k, v in ls.stats.items():
+            stats[k] = stats.get(k, 0) + v
+    stats['seconds'] = time.perf_counter() - t0
+    stats['gpu_launches'] = h.launch_count
+    return out, stats
+
+
+def run_shard(seeds, device, workers, kw, mode='lockstep', batch=512):
+    seeds = list(seeds)
+    if mode == 'sequential':
+        if workers <= 1 or len(seeds) <= 1:
+            return _worker((seeds, device, kw)), {}
+        import multiprocessing as mp
+        chunks = [seeds[i::workers] for i in range(workers)]
+        with mp.get_context('spawn').Pool(workers) as pool:
+            parts = pool.map(_worker, [(c, device, kw) for c in chunks if c])
+        out = [r for part in parts for r in part]
+        out.sort(key=lambda r: r['seed'])
+        return out, {}
     if workers <= 1 or len(seeds) <= 1:
-        return _worker((list(seeds), device, kw))
+        return _lockstep_worker((seeds, device, kw, batch))
     import multiprocessing as mp
-    chunks = [list(seeds[i::workers]) for i in range(workers)]
+    per = (len(seeds) + workers - 1) // workers
+    chunks = [seeds[i * per:(i + 1) * per] for i in range(workers)]
     with mp.get_context('spawn').Pool(workers) as pool:
-        parts = pool.map(_worker, [(c, device, kw) for c in chunks if c])
-    out = [r for part in parts for r in part]
-    out.sort(key=lambda r: r['seed'])
-    return out
+        parts = pool.map(_lockstep_worker, [(c, device, kw, batch) for c in chunks if c])
+    out = [r for part, _ in parts for r in part]
+    stats = {}
+    for _, st in parts:
+        for k, v in st.items():
+            stats[k] = max(stats.get(k, 0), v) if k == 'seconds' else stats.get(k, 0) + v
+    return out, stats
+
+
+class _UtilSampler:
+    """nvidia-smi utilization.gpu of one device while the replicas run (GPU-busy fraction of a host-bound driver)."""
+
+    def __init__(self, gpu):
+        import subprocess
+        import threading
+        self.vals = []
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=utilization.gpu', '--format=csv,noheader,nounits', '-lms', '250'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            try:
+                self.vals.append(float(line.strip()))
+            except ValueError:
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        return (sum(self.vals) / len(self.vals) / 100.0) if self.vals else None
 
 
 def main(argv=None):
@@ -98,7 +170,10 @@ def main(argv=None):
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--multi-opt', type=int, default=30)
     ap.add_argument('--multi-hyper', type=int, default=15)
-    ap.add_argument('--workers', type=int, default=1, help='worker processes per rank sharing its GPU')
+    ap.add_argument('--mode', default='lockstep', choices=['lockstep', 'sequential'],
+                    help='lockstep: all replicas of a worker advance together, one batched launch per SLSQP round; sequential: one episode after the other')
+    ap.add_argument('--workers', type=int, default=1, help='worker processes per rank sharing its GPU (each runs its replicas in lock step)')
+    ap.add_argument('--batch', type=int, default=512, help='replicas per lock-step batch inside a worker')
     a = ap.parse_args(argv)
     import torch
     import torch.distributed as dist
@@ -107,30 +182,46 @@ def main(argv=None):
     torch.cuda.set_device(local_rank)
     lo, hi = parallel.shard_range(a.replicas, rank, world)
     kw = dict(problem=a.problem, obj_setting=a.obj, n_iter=a.iters, multi_opt=a.multi_opt, multi_hyper=a.multi_hyper)
+    util = _UtilSampler(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
-    res = run_shard(range(lo, hi), local_rank, a.workers, kw)
+    res, stats = run_shard(range(lo, hi), local_rank, a.workers, kw, a.mode, a.batch)
     dt = time.perf_counter() - t0
+    busy = util.stop() if util else None
     # records: (objective of the final iterate, +inf when infeasible; global replica id) -> one all-gather -> arg-min
     h = api.Handle(local_rank)
     per = (a.replicas + world - 1) // world                              # equal record counts per rank (pad with +inf)
     score = torch.full((per,), float('inf'), dtype=torch.float64, device=h.device)
     idx = torch.full((per,), -1, dtype=torch.int64, device=h.device)
+    allv = torch.full((per,), float('nan'), dtype=torch.float64, device=h.device)
     for j, r in enumerate(res):
         score[j] = r['objective'] if r['feasible'] else float('inf')
         idx[j] = r['seed']
+        allv[j] = r['objective']
     rec = parallel.allgather_records(h.pack_best(score, idx))
     best_v, best_seed, _ = parallel.global_argmin(rec)
     tmax = torch.tensor([dt], dtype=torch.float64, device=h.device)
+    tot = torch.tensor([float(stats.get(k, 0)) for k in ('slsqp_calls_fit', 'slsqp_calls_acq', 'nlml_evals', 'k4_points', 'gpu_launches')] +
+                       [float(sum(1 for r in res if r.get('dead')))], dtype=torch.float64, device=h.device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     if rank == 0:
         s, i = parallel.unpack_records(rec)
         ok = (i >= 0) & torch.isfinite(s)
-        print(json.dumps({'metric': 'RTO replicas/s', 'value': a.replicas / float(tmax[0]), 'replicas': a.replicas, 'n_gpus': world,
-                          'workers_per_gpu': a.workers, 'problem': a.problem, 'iters': a.iters, 'seconds': float(tmax[0]),
-                          'feasible_fraction': float(ok.sum()) / a.replicas, 'best_objective': best_v, 'best_replica': best_seed,
-                          'mean_feasible_objective': float(s[ok].mean()) if bool(ok.any()) else None,
-                          'gpu_launches_rank0_gather': h.launch_count}))
+        sec = float(tmax[0])
+        sign = -1.0 if a.problem == 'wo' else 1.0            # Williams-Otto: objective = -profit
+        line = {'metric': 'RTO replicas/s', 'value': a.replicas / sec, 'replicas': a.replicas, 'n_gpus': world, 'mode': a.mode,
+                'workers_per_gpu': a.workers, 'lockstep_batch': a.batch if a.mode == 'lockstep' else None, 'problem': a.problem, 'iters': a.iters,
+                'multi_opt': a.multi_opt, 'multi_hyper': a.multi_hyper, 'seconds': sec, 'feasible_fraction': float(ok.sum()) / a.replicas,
+                'best_objective': best_v, 'best_replica': best_seed,
+                'mean_feasible_objective': float(s[ok].mean()) if bool(ok.any()) else None,
+                'best_profit' if a.problem == 'wo' else 'best_f': sign * best_v,
+                'mean_feasible_profit' if a.problem == 'wo' else 'mean_feasible_f': (sign * float(s[ok].mean())) if bool(ok.any()) else None,
+                'optimum': 75.81 if a.problem == 'wo' else 0.145,
+                'slsqp_calls': {'fit': int(tot[0]), 'acquisition': int(tot[1])}, 'nlml_evals': int(tot[2]), 'k4_point_evals': int(tot[3]),
+                'gpu_launches': int(tot[4]), 'aborted_replicas': int(tot[5]), 'gpu_busy_fraction_rank0': busy,
+                'collective': 'all-gather of (objective, replica id) records + redundant arg-min' if world > 1 else 'none'}
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -148,7 +148,9 @@ def minimize_arrays(fun_batch, X0, LB, UB, con_batch=None, m_ineq=0, ftol=1e-6, 
     allk = np.arange(K)
     evaluate(allk, allk)
     active = allk
+    calls = 0
     while active.size:
+        calls += int(active.size)
         fxl = FX[active].tolist()
         modes = np.empty(active.size, dtype=np.int64)
         for j, k in enumerate(active.tolist()):
@@ -159,7 +161,7 @@ def minimize_arrays(fun_batch, X0, LB, UB, con_batch=None, m_ineq=0, ftol=1e-6, 
         active = active[np.abs(modes) == 1]
     status = np.array([st['mode'] for st in states], dtype=np.int64)
     nit = np.array([st['iter'] for st in states], dtype=np.int64)
-    return dict(x=X, fun=FX, status=status, nit=nit, nfev=NFEV, njev=NJEV, jac=G, mult=MULT[:, :m])
+    return dict(x=X, fun=FX, status=status, nit=nit, nfev=NFEV, njev=NJEV, jac=G, mult=MULT[:, :m], slsqp_calls=calls)
 
 
 def minimize_batch(fun_batch, x0s, bounds, con_batch=None, m_ineq=0, ftol=1e-6, maxiter=100, eps=_EPS, inst_ids=None):
