@@ -243,6 +243,54 @@ class Handle:
                     y_mean=nz['y_mean'], y_std=nz['y_std'], logdet=logdet, status=st)
 
 
+    def fit(self, X, Y, multi_hyper=15, noise=None, jitter=JITTER_NLML, ftol=1e-12, maxiter=10000):
+        """Batched sibling of GP_model(X, Y, 'RBF', multi_hyper, noise=...) for B independent single-output GPs
+        (reference: sub_uts/utilities_2.py:28-44, 120-177): X[B,n,d], Y[B,n] (device tensors or NumPy arrays).
+
+        normalise (kernel) -> B x multi_hyper Sobol starts in the reference's log-hyper box (:131-158; a known noise
+        variance `noise` (scalar or [B]) pins the last bound to 0.5 log(noise / y_std^2) +- 1e-3, :149-154) -> all
+        B x S SLSQP instances in lock step over gprto_nlml_indexed_host (one launch per round; SciPy's SLSQP routine,
+        tol 1e-12, forward differences, as :160-161) -> gprto_argmin over the starts (first minimum wins, :166) ->
+        gprto_factor at the selected hyper-parameters (:168-175).
+        Returns the gp dict posterior_acq consumes plus theta[B,d+2], localval[B,S] (NumPy), minindex[B] (NumPy)."""
+        from . import slsqp_batch
+        from .compat import sobol_seq
+        T = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)  # noqa: E731
+        X, Y = T(X).contiguous(), T(Y).contiguous()
+        B, n, d = X.shape
+        S = int(multi_hyper)
+        nz = self.normalise(X, Y)
+        lb = np.tile(np.array([-5.0] * (d + 1) + [-8.0]), (B, 1))
+        ub = np.tile(np.array([5.0] * (d + 1) + [-4.0]), (B, 1))
+        if noise is not None:
+            centre = 0.5 * np.log(np.broadcast_to(np.asarray(noise, dtype=float), (B,)) / nz['y_std'].cpu().numpy() ** 2)
+            lb[:, -1], ub[:, -1] = centre - 0.001, centre + 0.001
+        sob = sobol_seq.i4_sobol_generate(d + 2, S)
+        LB, UB = np.repeat(lb, S, axis=0), np.repeat(ub, S, axis=0)
+        x0 = LB + (UB - LB) * np.tile(sob, (B, 1))                          # instance (b, j) = b * S + j
+        owner = np.repeat(np.arange(B, dtype=np.int32), S)
+        failed = np.zeros(B, dtype=bool)
+
+        def fun_batch(inst, P):
+            out, st = self.nlml_indexed_host(nz['Xn'], nz['Yn'], owner[inst], P, jitter=jitter)
+            if st.any():            # the reference raises numpy.linalg.LinAlgError here (:107); reported per GP in `status`
+                bad = np.flatnonzero(st)
+                failed[owner[inst][bad]] = True
+                out[bad] = 1e300
+            return out
+
+        res = slsqp_batch.minimize_arrays(fun_batch, x0, LB, UB, ftol=ftol, maxiter=maxiter)
+        localval = res['fun'].reshape(B, S)
+        _, best = self.argmin(T(localval))
+        best_h = best.cpu().numpy()
+        theta = T(res['x'].reshape(B, S, d + 2)[np.arange(B), best_h])
+        invK, alpha, logdet, st = self.factor(nz['Xn'], nz['Yn'], theta)
+        st = st | T(failed.astype(np.int32)).to(torch.int32)
+        return dict(Xn=nz['Xn'], Yn=nz['Yn'], invK=invK, alpha=alpha, theta=theta, x_mean=nz['x_mean'], x_std=nz['x_std'],
+                    y_mean=nz['y_mean'], y_std=nz['y_std'], logdet=logdet, status=st, localval=localval, localsol=res['x'].reshape(B, S, d + 2),
+                    minindex=best_h, slsqp_calls=res['slsqp_calls'])
+
+
 _default = {}
 
 
