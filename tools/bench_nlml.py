@@ -39,11 +39,19 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
     bv, bi = h.argmin(nll)
+    check = None
+    if a.path not in (0, 1):            # cross-check against the shared-memory kernel on a slice
+        h.set_option('k3_path', 1)
+        nb = min(a.B, 64)
+        ref, rst = h.nlml(nz['Xn'][:nb].contiguous(), nz['Yn'][:nb].contiguous(), w['theta'][:nb].contiguous())
+        ok = (rst == 0) & (st[:nb] == 0)
+        check = {'max_rel_diff_vs_generic': float(((nll[:nb] - ref).abs() / ref.abs().clamp(min=1.0))[ok].max()),
+                 'status_mismatch': int(((rst == 0) != (st[:nb] == 0)).sum())}
     F = a.n ** 3 / 3 + 2 * a.n ** 2 + (a.n ** 2 / 2) * (3 * a.d + 2) + 4 * a.n
     evals = a.B * a.S
     print(json.dumps({'metric': 'NLML evals/s (FP64, batched)', 'value': evals / (ms * 1e-3), 'ms_per_sweep': ms, 'B': a.B, 'S': a.S, 'n': a.n,
-                      'd': a.d, 'path': {0: 'auto', 1: 'generic', 2: 'reg'}[a.path], 'flops_per_eval': F, 'achieved_tflops': evals * F / (ms * 1e-3) / 1e12,
-                      'failed': int((st != 0).sum()), 'nan': int(torch.isnan(nll).sum()), 'argmin_hist_first8': bi[:8].tolist()}))
+                      'd': a.d, 'path': {0: 'auto', 1: 'generic', 2: 'reg', 3: 'service-scheduler', 4: 'look-ahead'}[a.path], 'flops_per_eval': F, 'achieved_tflops': evals * F / (ms * 1e-3) / 1e12,
+                      'failed': int((st != 0).sum()), 'nan': int(torch.isnan(nll).sum()), 'argmin_hist_first8': bi[:8].tolist(), 'check': check}))
 
 
 if __name__ == '__main__':
