@@ -172,7 +172,7 @@ def main(argv=None):
     ap.add_argument('--multi-hyper', type=int, default=15)
     ap.add_argument('--mode', default='lockstep', choices=['lockstep', 'sequential'],
                     help='lockstep: all replicas of a worker advance together, one batched launch per SLSQP round; sequential: one episode after the other')
-    ap.add_argument('--workers', type=int, default=1, help='worker processes per rank sharing its GPU (each runs its replicas in lock step)')
+    ap.add_argument('--workers', type=int, default=1, help='worker processes per rank sharing its GPU (each runs its replicas in lock step); 0 = host cores / ranks')
     ap.add_argument('--batch', type=int, default=512, help='replicas per lock-step batch inside a worker')
     a = ap.parse_args(argv)
     import torch
@@ -180,6 +180,8 @@ def main(argv=None):
     from gp_rto_ei_b200 import api, parallel
     rank, local_rank, world = parallel.init()
     torch.cuda.set_device(local_rank)
+    if a.workers <= 0:
+        a.workers = max(1, len(os.sched_getaffinity(0)) // world)
     lo, hi = parallel.shard_range(a.replicas, rank, world)
     kw = dict(problem=a.problem, obj_setting=a.obj, n_iter=a.iters, multi_opt=a.multi_opt, multi_hyper=a.multi_hyper)
     util = _UtilSampler(local_rank) if rank == 0 else None
@@ -211,7 +213,7 @@ def main(argv=None):
         sec = float(tmax[0])
         sign = -1.0 if a.problem == 'wo' else 1.0            # Williams-Otto: objective = -profit
         line = {'metric': 'RTO replicas/s', 'value': a.replicas / sec, 'replicas': a.replicas, 'n_gpus': world, 'mode': a.mode,
-                'workers_per_gpu': a.workers, 'lockstep_batch': a.batch if a.mode == 'lockstep' else None, 'problem': a.problem, 'iters': a.iters,
+                'workers_per_gpu': a.workers, 'host_cores': len(os.sched_getaffinity(0)), 'lockstep_batch': a.batch if a.mode == 'lockstep' else None, 'problem': a.problem, 'iters': a.iters,
                 'multi_opt': a.multi_opt, 'multi_hyper': a.multi_hyper, 'seconds': sec, 'feasible_fraction': float(ok.sum()) / a.replicas,
                 'best_objective': best_v, 'best_replica': best_seed,
                 'mean_feasible_objective': float(s[ok].mean()) if bool(ok.any()) else None,
