@@ -13,7 +13,9 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.environ.get('GPRTO_LIB_OUT', os.path.join(HERE, 'libgprto.so'))
 SOURCES = ['gprto_api.cu', 'k3_inst.cu', 'k2_inst.cu', 'k4_inst_a.cu', 'k4_inst_b.cu', 'k4_inst_c.cu', 'k4_inst_d.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
+# -fmad=false: a*b+c stays two roundings unless fma() is written - the arithmetic is SPECIFIED (gprto_det_math.h) so that the
+# ordered CPU twin (oracle/twin/) reproduces it bit for bit; every hot loop uses explicit fma / DMMA, so this costs nothing
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-fmad=false', '-Xcompiler', '-fPIC']
 
 
 def _deps():

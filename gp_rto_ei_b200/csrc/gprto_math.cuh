@@ -4,39 +4,14 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "gprto_det_math.h"
+
 namespace gprto {
 
-// exp(a) for finite a <= ~700.  Cody-Waite reduction a = n*ln2 + r, |r| <= ln2/2, degree-11 polynomial
-// (Chebyshev-node fit; max relative error 1.7e-17 in exact arithmetic, measured < 1 ulp in FP64),
-// scaling by exponent-field addition.  15 FP64-pipe instructions against ~21 for libdevice exp(): the
-// cross-covariance needs n exponentials per candidate, which is ~1/3 of the FP64 work of K4.
-// a < -700 returns 0 (the reference would return a value below 1e-304 there).
-__device__ __forceinline__ double exp_fast(double a) {
-  const double LOG2E = 1.4426950408889634074;
-  const double LN2_HI = 6.93147180369123816490e-01;   // high part of ln2 (low 21 bits zero)
-  const double LN2_LO = 1.90821492927058770002e-10;
-  const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: round-to-nearest-integer shifter
-  double t = fma(a, LOG2E, MAGIC);
-  int n = __double2loint(t);
-  double nf = t - MAGIC;
-  double r = fma(nf, -LN2_HI, a);
-  r = fma(nf, -LN2_LO, r);
-  double p = 2.5110049204818658e-08;
-  p = fma(p, r, 2.763265472252779e-07);
-  p = fma(p, r, 2.755724088722987e-06);
-  p = fma(p, r, 2.4801485441561313e-05);
-  p = fma(p, r, 0.00019841269890076403);
-  p = fma(p, r, 0.0013888888952352863);
-  p = fma(p, r, 0.008333333333319589);
-  p = fma(p, r, 0.04166666666648795);
-  p = fma(p, r, 0.1666666666666668);
-  p = fma(p, r, 0.5000000000000019);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  int hi = __double2hiint(p) + (int)((unsigned)n << 20);
-  double res = __hiloint2double(hi, __double2loint(p));
-  return a < -700.0 ? 0.0 : res;
-}
+// exp / log / rsqrt / erfc / acquisition live in gprto_det_math.h: IEEE operations and integer bit manipulation only, so that
+// the ordered CPU twin (oracle/twin/) reproduces them bit for bit.  The library is compiled with -fmad=false: a*b+c is two
+// roundings unless fma() is written, on the device exactly as on the host.
+__device__ __forceinline__ double exp_fast(double a) { return exp_det(a); }
 
 // numpy.argmin ordering on (value, index): a NaN beats any number, ties go to the lower index.
 __device__ __forceinline__ bool better(double va, int64_t ia, double vb, int64_t ib) {
@@ -45,36 +20,11 @@ __device__ __forceinline__ bool better(double va, int64_t ia, double vb, int64_t
   return va < vb || (va == vb && ia < ib);
 }
 
-// The three acquisition scores of ITR_GP_RTO.GP_obj_f (reference: sub_uts/utilities_2.py:485-504).
-// mean/var are the de-normalised GP outputs, prior = obj_model(x).  EI keeps the reference's quirk
-// Z := 0 when sigma == 0 and scipy's normal pdf/cdf definitions (pdf = exp(-Z^2/2)/sqrt(2 pi),
-// cdf = ndtr(Z) = 0.5*erfc(-Z/sqrt 2)).
 __device__ __forceinline__ double acquisition(int acq, double mean, double var, double prior, double f_best) {
-  const double mu = prior + mean;
-  if (acq == 1) return mu;
-  const double sigma = sqrt(var);
-  if (acq == 2) return mu - 3.0 * sigma;
-  const double delta = f_best - mu;
-  const double z = (sigma == 0.0) ? 0.0 : delta / sigma;
-  const double pdf = exp(-0.5 * z * z) * 0.39894228040143267794;
-  const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
-  return -(sigma * pdf + delta * cdf);
+  return acquisition_det(acq, mean, var, prior, f_best);
 }
 
-// 1/sqrt(x) for normal positive x: hardware seed (rsqrt.approx.f64, ~2^-22) + two Newton steps (6 dependent FP64
-// instructions, relative error ~1e-16).  Non-positive or NaN x yields NaN/inf, which the callers flag beforehand.
-__device__ __forceinline__ double rsqrt_fast(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = 0.5 * x;
-  double u = h * y;
-  double t = fma(-u, y, 0.5);
-  y = fma(y, t, y);
-  u = h * y;
-  t = fma(-u, y, 0.5);
-  y = fma(y, t, y);
-  return y;
-}
+__device__ __forceinline__ double rsqrt_fast(double x) { return rsqrt_det(x); }
 
 // Counter-based trust-region sampler shared by K4's fused mode and gprto_sample_candidates: candidate c of GP b is a
 // pure function of (seed, b, c).  shape 0: uniform in the box [-1,1]^D; shape 1: uniform in the unit ball (Gaussian
@@ -149,7 +99,7 @@ __device__ __forceinline__ void tr_point(uint64_t seed, int64_t b, int64_t c, in
     if (!(ball > 0.0) || n2 <= ball * ball) break;
   }
   if (ball > 0.0 && n2 > ball * ball) {
-    const double sc = 0.999 * ball * rsqrt(n2);
+    const double sc = 0.999 * ball * rsqrt_det(n2);
 #pragma unroll
     for (int dd = 0; dd < D; ++dd) off[dd] *= sc;
   }

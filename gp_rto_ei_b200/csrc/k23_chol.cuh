@@ -15,14 +15,14 @@ inline size_t ch_smem_bytes(int n, int d) {
   return sizeof(double) * (size_t(n) * ch_ld(n) + size_t(n) * d + 3 * size_t(n) + 2 * CH_MAXD + 8);
 }
 
-// K_ij = exp(2 theta_sf + sum_dd (x_i - x_j)^2 * nhw_dd),  nhw_dd = -1/(2 W_dd) = -0.5 exp(-2 theta_dd).
+// K_ij = exp_det(2 theta_sf + sum_dd (x_i - x_j)^2 * nhw_dd),  nhw_dd = -1/(2 W_dd) = -0.5 exp_det(-2 theta_dd).
 // The difference is formed BEFORE scaling so its rounding error stays relative to |x_i - x_j| (as in the
 // reference's cdist); scaling the points first loses ~length-scale^-1 digits on near-duplicate points, which
 // cond(K) then amplifies in the NLML.
 __device__ __forceinline__ void ch_stage_inputs(const double* __restrict__ Xn, const double* __restrict__ theta,
                                                 int n, int d, double* Xs, double* nhw) {
   for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xs[e] = Xn[e];
-  if (threadIdx.x < d) nhw[threadIdx.x] = -0.5 * exp(-2.0 * theta[threadIdx.x]);
+  if (threadIdx.x < d) nhw[threadIdx.x] = -0.5 * exp_det(-2.0 * theta[threadIdx.x]);
 }
 
 __device__ __forceinline__ void ch_build_K(const double* Xs, const double* nhw, int n, int d, double c0,
@@ -71,7 +71,7 @@ __device__ __forceinline__ void ch_cholesky(double* A, int n, int ld, double* ri
     __syncthreads();
   }
   double lg = 0.0;
-  for (int k = tid; k < n; k += nt) lg += log(A[k * ld + k]);
+  for (int k = tid; k < n; k += nt) lg += log_det(A[k * ld + k]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, off);
   if ((tid & 31) == 0) atomicAdd(s_logdet, lg);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(CH_THREADS) nlml_generic_kernel(int S, int n, 
   ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = Yn[b * n + i];
   __syncthreads();
-  const double sn2 = exp(2.0 * theta[d + 1]);
+  const double sn2 = exp_det(2.0 * theta[d + 1]);
   ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], sn2 + jitter, A, ld);
   __syncthreads();
   ch_cholesky(A, n, ld, rinv, &s_info, &s_logdet);
@@ -146,8 +146,8 @@ __device__ __forceinline__ double cov_entry(const double* Xs, const double* nhw,
   }
   if (kind == 0) return exp_fast(c0 + acc);
   const double dist = -2.0 * acc, r = sqrt(dist);
-  if (kind == 1) return sf2 * (1.0 + 1.7320508075688772 * r) * exp(-1.7320508075688772 * r);
-  return sf2 * (1.0 + 2.23606797749979 * r + (5.0 / 3.0) * dist) * exp(-2.23606797749979 * r);
+  if (kind == 1) return sf2 * (1.0 + 1.7320508075688772 * r) * exp_det(-1.7320508075688772 * r);
+  return sf2 * (1.0 + 2.23606797749979 * r + (5.0 / 3.0) * dist) * exp_det(-2.23606797749979 * r);
 }
 
 inline size_t cov_smem_bytes(int n, int d, bool tiled) {
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(CH_THREADS) cov_kernel(int S, int n, int d, co
   const double* theta = theta_all + bs * (d + 2);
   ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   __syncthreads();
-  const double diag = (add_noise ? exp(2.0 * theta[d + 1]) : 0.0) + jitter;
+  const double diag = (add_noise ? exp_det(2.0 * theta[d + 1]) : 0.0) + jitter;
   const double c0 = 2.0 * theta[d];
-  const double sf2 = exp(c0);
+  const double sf2 = exp_det(c0);
   double* Kout = K + bs * int64_t(n) * n;
   // warp w evaluates rows w, w + nwarps, ...: lanes stride over the columns j <= i (no index decoding, row data reused)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CH_THREADS) factor_generic_kernel(int n, int d
   ch_stage_inputs(Xn + b * int64_t(n) * d, theta, n, d, Xs, nhw);
   for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = Yn[b * n + i];
   __syncthreads();
-  ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], exp(2.0 * theta[d + 1]) + jitter, A, ld);
+  ch_build_K(Xs, nhw, n, d, 2.0 * theta[d], exp_det(2.0 * theta[d + 1]) + jitter, A, ld);
   __syncthreads();
   ch_cholesky(A, n, ld, rinv, &s_info, &s_logdet);
   __syncthreads();

@@ -60,7 +60,7 @@ k2_factor_la_kernel(int n, int d_rt, const double* __restrict__ Xn, const double
 
   for (int e = tid; e < NP * d; e += THREADS) Xs[e] = (e / d) < n ? Xn[b * int64_t(n) * d + e] : 0.0;
   for (int e = tid; e < NP; e += THREADS) ys[e] = e < n ? Yn[b * n + e] : 0.0;
-  if (tid < d) nhw[tid] = -0.5 * exp(-2.0 * theta[tid]);
+  if (tid < d) nhw[tid] = -0.5 * exp_det(-2.0 * theta[tid]);
   if (tid == 0) s_info = 0;
   for (int e = tid; e < TILES; e += THREADS) {
     int J = 0;
@@ -86,11 +86,11 @@ k2_factor_la_kernel(int n, int d_rt, const double* __restrict__ Xn, const double
       if (lane == 0 && info) s_info = info;
       k3la_bar_sync(2, ATHREADS);                                       // Y(kb)
     }
-    if (lane == 0) misc[0] = log(pm) + double(pe) * 0.693147180559945309417;
+    if (lane == 0) misc[0] = log_det(pm) + double(pe) * 0.693147180559945309417;
   } else {
     const int uw = w, utid = 32 * uw + lane;
     const double c0 = 2.0 * theta[d];
-    const double diag_add = exp(2.0 * theta[d + 1]) + jitter;
+    const double diag_add = exp_det(2.0 * theta[d + 1]) + jitter;
     double C0[SLOTS], C1[SLOTS];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {

@@ -95,7 +95,7 @@ __device__ __forceinline__ void k3_diag_tile(double* tile, int ldp, const double
     zs[lane] = z;
     zq = z * z;
     rinv[lane] = tmine * myS;
-    lg = 2.0 * log(mydp * tmine);
+    lg = 2.0 * log_det(mydp * tmine);
   }
 #pragma unroll
   for (int off = 1; off < 8; off <<= 1) {
@@ -187,7 +187,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
 
   for (int e = tid; e < NP * d; e += THREADS) Xs[e] = (e / d) < n ? Xn[b * int64_t(n) * d + e] : 0.0;
   for (int e = tid; e < NP; e += THREADS) ys[e] = e < n ? Yn[b * n + e] : 0.0;
-  if (tid < d) nhw[tid] = -0.5 * exp(-2.0 * theta[tid]);
+  if (tid < d) nhw[tid] = -0.5 * exp_det(-2.0 * theta[tid]);
   if (tid == 0) { s_info = 0; *quad_s = 0.0; }
   for (int e = tid; e < TILES; e += THREADS) {      // column-major tile order: tau = off(J) + (I - J), off(J) = J NT - J(J-1)/2
     int J = 0;
@@ -230,7 +230,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
       const int inf = s_info;
       status[bs] = inf;
       // log det = log(prod pivots) = log(mantissa) + exponent * ln 2
-      nll[bs] = inf == 0 ? *quad_s + log(pm) + double(pe) * 0.693147180559945309417 : CUDART_NAN;
+      nll[bs] = inf == 0 ? *quad_s + log_det(pm) + double(pe) * 0.693147180559945309417 : CUDART_NAN;
     }
     return;
   }
@@ -238,7 +238,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   // ================================ update warps ================================
   const int uw = (IDLE_W >= 0 && w > IDLE_W) ? w - 1 : w, utid = 32 * uw + lane;
   const double c0 = 2.0 * theta[d];
-  const double diag_add = exp(2.0 * theta[d + 1]) + jitter;
+  const double diag_add = exp_det(2.0 * theta[d + 1]) + jitter;
   double C0[SLOTS], C1[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {

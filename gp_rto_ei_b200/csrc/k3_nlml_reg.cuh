@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
 
   for (int e = tid; e < NP * d; e += THREADS) Xs[e] = (e / d) < n ? Xn[b * int64_t(n) * d + e] : 0.0;
   for (int e = tid; e < NP; e += THREADS) ys[e] = e < n ? Yn[b * n + e] : 0.0;
-  if (tid < d) nhw[tid] = -0.5 * exp(-2.0 * theta[tid]);
+  if (tid < d) nhw[tid] = -0.5 * exp_det(-2.0 * theta[tid]);
   if (tid == 0) s_info = 0;
   __syncthreads();
 
   const double c0 = 2.0 * theta[d];
-  const double diag_add = exp(2.0 * theta[d + 1]) + jitter;
+  const double diag_add = exp_det(2.0 * theta[d + 1]) + jitter;
   const int rowA = w, rowB = NT - 1 - w;
 
   // ---- build the tiles of K in registers (branch-free padding: identity block outside n)
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(16 * NT, (NT >= 12 ? 2 : (NT >= 6 ? 4 : 8))) k
         zs[lane] = z;
         zq = z * z;
         rinv_s[lane] = tmine * myS;                                                // 1/L_cc = rsqrt(d'_c / S_c)
-        lg = 2.0 * log(mydp * tmine);                                              // log pivot = 2 log L_cc
+        lg = 2.0 * log_det(mydp * tmine);                                              // log pivot = 2 log L_cc
       }
 #pragma unroll
       for (int off = 1; off < 8; off <<= 1) {

@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(K4_THREADS, (NB <= 8 ? K4_MINB : 1)) k4_dmma_k
   if (tid < D) {
     cs[tid] = 1.0 / p.x_std[b * D + tid];
     cm[tid] = p.x_mean[b * D + tid];
-    sc[tid] = -0.5 * exp(-2.0 * theta[tid]);      // -1/(2 W_d)
+    sc[tid] = -0.5 * exp_det(-2.0 * theta[tid]);      // -1/(2 W_d)
   }
   if (tid == 0) {
     scal[0] = 2.0 * theta[D];
-    scal[1] = exp(2.0 * theta[D]);
+    scal[1] = exp_det(2.0 * theta[D]);
     scal[2] = p.y_std[b];
     scal[3] = p.y_mean[b];
     scal[4] = p.f_best ? p.f_best[b] : 0.0;
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
   __shared__ double red_s[K4G_THREADS / 32];
   __shared__ int64_t red_i[K4G_THREADS / 32];
   double invW[K4G_MAXD];
-  for (int dd = 0; dd < d; ++dd) invW[dd] = exp(-2.0 * theta[dd]);
-  const double sf2 = exp(2.0 * theta[d]);
+  for (int dd = 0; dd < d; ++dd) invW[dd] = exp_det(-2.0 * theta[dd]);
+  const double sf2 = exp_det(2.0 * theta[d]);
   const double y_std = p.y_std[b], y_mean = p.y_mean[b];
   const double f_best = p.f_best ? p.f_best[b] : 0.0;
   const int64_t c_begin = int64_t(blockIdx.y) * p.chunk;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(K4G_THREADS) k4_generic_kernel(const K4Params 
         const double df = x[dd] - Xn[j * d + dd];
         s = fma(df * df, invW[dd], s);
       }
-      k[j] = sf2 * exp(-0.5 * s);
+      k[j] = sf2 * exp_det(-0.5 * s);
       mn = fma(k[j], alpha[j], mn);
     }
     double q = 0.0;
