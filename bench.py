@@ -344,14 +344,15 @@ def cfg4_setup(c, B, S, n, d, seed):
     return st
 
 
-def cfg4_step(c, st, B, S, n, d, lo):
-    """K3 over all (GP, start) pairs, per-GP arg-min over the starts (utilities_2.py:166), and the gather of (nll_best, idx)."""
+def cfg4_step(c, st, B, S, n, d, lo, gather=True):
+    """K3 over all (GP, start) pairs, per-GP arg-min over the starts (utilities_2.py:166), and the gather of (nll_best, idx).
+    gather=False: rank-local call (the parity sample runs on rank 0 alone and must not enter a collective)."""
     from gp_rto_ei_b200 import api, parallel
     lib, hp, P, h = c.h.lib, c.h._h, api._ptr, c.h
     nz, w = st['nz'], st['w']
     api._lib.check(lib.gprto_nlml(hp, B, S, n, d, P(nz['Xn']), P(nz['Yn']), P(w['theta']), 1e-8, P(st['nll']), P(st['status']), h._stream()), 'gprto_nlml')
     api._lib.check(lib.gprto_argmin(hp, B, S, P(st['nll']), P(st['best_v']), P(st['best_i']), h._stream()), 'gprto_argmin')
-    if c.world > 1:
+    if c.world > 1 and gather:
         api._lib.check(lib.gprto_pack_best(hp, B, P(st['best_v']), P(st['best_i']), 0, P(st['rec']), h._stream()), 'gprto_pack_best')
         return parallel.allgather_records(st['rec'])
     return None
@@ -416,7 +417,7 @@ def run_cfg4(args, c):
     from oracle import gp_oracle as O
     import numpy as np
     st = cfg4_setup(c, 4, S, n, d, seed=1 + 1000 * c.rank)
-    cfg4_step(c, st, 4, S, n, d, 0)
+    cfg4_step(c, st, 4, S, n, d, 0, gather=False)
     nll = st['nll'].cpu().numpy(); stat = st['status'].cpu().numpy()
     Xh, yh, th = st['w']['X'].cpu().numpy(), st['w']['y'].cpu().numpy(), st['w']['theta'].cpu().numpy()
     worst, mism, worst_cond_ok = 0.0, 0, 0.0

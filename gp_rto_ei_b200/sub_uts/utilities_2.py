@@ -166,6 +166,20 @@ class GP_model:
         # final factor: Kopt = K + sn2*I, no jitter (:173-175); invK and alpha = invK*y stay on the device too
         Xb = self._Xn.unsqueeze(0).expand(ny, self.n_point, d).contiguous()
         invK, alpha, logdet, st = self._h.factor(Xb, self._Yn, _dev(theta, self._h), jitter=0.0)
+        if int(st.abs().sum()) != 0:
+            # The reference inverts Kopt by LU (np.linalg.solve, :175), which survives a numerically singular but noisy Kopt
+            # (near-duplicate inputs with the noise pinned around 1e-7) where a Cholesky factorisation reports a non-positive
+            # pivot.  With sn2 > 0 the matrix is positive definite in exact arithmetic, so retry with a diagonal shift far below
+            # the noise level and say so; an exactly singular Kopt (sn2 == 0) raises, as LAPACK does for the reference.
+            sf2, sn2 = np.exp(2 * theta[:, d]), np.exp(2 * theta[:, d + 1])
+            if np.all(sn2 > 0):
+                for rel in (1e-12, 1e-10, 1e-8):
+                    shift = float(rel * sf2.max())
+                    invK, alpha, logdet, st = self._h.factor(Xb, self._Yn, _dev(theta, self._h), jitter=shift)
+                    if int(st.abs().sum()) == 0:
+                        import warnings
+                        warnings.warn('final factor: Kopt is numerically singular; factorised with a diagonal shift of %.1e' % shift, RuntimeWarning)
+                        break
         self._h.raise_on_failure(st, 'determine_hyperparameters (final factor)')
         self._gp = dict(Xn=Xb, invK=invK, alpha=alpha, theta=_dev(theta, self._h),
                         x_mean=_dev(np.tile(self.X_mean, (ny, 1)), self._h), x_std=_dev(np.tile(self.X_std, (ny, 1)), self._h),

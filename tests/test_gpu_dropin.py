@@ -165,6 +165,25 @@ def test_gp_model_inference_api(u2):
         gp2 = u2.GP_model(Xd, np.vstack([Y, Y[:1]]), 'RBF', multi_hyper=1, _theta=np.array([0.0, 0.0, 0.0, -400.0]))
 
 
+def test_final_factor_survives_a_numerically_singular_but_noisy_kernel_matrix(u2):
+    """The reference inverts Kopt by LU (utilities_2.py:175), which does not fail on near-duplicate inputs with a tiny but
+    positive noise; the drop-in's Cholesky factor retries with a diagonal shift far below the noise level instead of aborting
+    the episode (exactly singular Kopt, sn2 == 0, still raises - see test_gp_model_inference_api)."""
+    import warnings
+    g = load_golden('pickle_gps.npz')
+    X, Y = g['X1'], g['Y1']
+    Xd = np.vstack([X, X[:2] + 1e-13])                     # two near-duplicates
+    Yd = np.vstack([Y, Y[:2]])
+    theta = g['hypopt1'][:, 0].copy()
+    theta[-1] = 0.5 * np.log(1e-20)                         # noise variance 1e-20 > 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        gp = u2.GP_model(Xd, Yd, 'RBF', multi_hyper=1, _theta=theta)
+    assert np.isfinite(gp.invKopt[0]).all()
+    mean, var = gp.GP_inference_np(X[5])
+    assert np.isfinite(mean).all() and np.isfinite(var).all()
+
+
 @pytest.mark.parametrize('tag,acq,noisy', [('noiseless_ei', 3, False), ('noisy_ei', 3, True), ('noiseless_lcb', 2, False)])
 def test_rto_episode_matches_reference(u2, tag, acq, noisy):
     """Short seeded episode on the toy problem (arguments of run_simple/main_simple.py:179-206, fewer iterations):
@@ -172,8 +191,9 @@ def test_rto_episode_matches_reference(u2, tag, acq, noisy):
     sensitivity.  Bit-identity of the iterates is not attainable: SLSQP's forward differences (step 1.5e-8, tol 1e-12)
     amplify last-bit differences of any two correct GP evaluations (SURVEY.md par. 7.3-1).  The golden file therefore
     also holds the same episode of the reference with its NLML / posterior nudged by ONE ulp; the spread of its iterates
-    under that nudge (5e-4 / 6e-8 / 7e-2 for the three cases) is the yardstick: ours must stay within 100x of it
-    (floor 1e-5), i.e. the GPU path behaves like a last-bits perturbation of the NumPy path."""
+    under that nudge (5e-4 / 6e-8 / 7e-2 for the three cases) is the yardstick: ours must stay within 10x of it
+    (floor 1e-6), i.e. the GPU path behaves like a last-bits perturbation of the NumPy path.  (Bit-identity is asserted
+    where it is attainable: GPU vs the ordered CPU twin of the kernels, tests/test_gpu_twin.py.)"""
     from gp_rto_ei_b200.sub_uts import systems as S
     g = load_golden('rto_simple.npz')
     np.random.seed(0); random.seed(0)
@@ -202,7 +222,7 @@ def test_rto_episode_matches_reference(u2, tag, acq, noisy):
     assert X_opt.shape == g[tag + '_X_opt'].shape and y_opt.shape == g[tag + '_y_opt'].shape
     sens = np.abs(g[tag + '_X_opt_ulp'] - g[tag + '_X_opt']).max()
     print('[rto %s] reference one-ulp self-sensitivity: %.3e' % (tag, sens))
-    tol = max(100 * sens, 1e-5)
+    tol = max(10 * sens, 1e-6)
     assert np.abs(X_opt - g[tag + '_X_opt']).max() < tol
     if not noisy:
         assert np.abs(y_opt - g[tag + '_y_opt']).max() < 10 * tol
@@ -249,8 +269,8 @@ def test_replica_driver_is_reproducible_per_seed(u2):
 def test_rto_episode_williams_otto_configuration(u2, tag, acq, noisy):
     """Config 2 (run_WO/main_WO_prior_EI.py): 1 + 2 GPs per iteration, scale_inputs=True (ellipse start sampling), model
     prior, known noise.  Golden = the reference's own ITR_GP_RTO / GP_model driven with the same NumPy plant callables.
-    Same criterion as the toy problem: identical trust-region / backtrack signature, iterates within 100x the reference's
-    one-ulp self-sensitivity (floor 1e-5 in inputs that span [4,7] x [70,100])."""
+    Same criterion as the toy problem: identical trust-region / backtrack signature, iterates within 10x the reference's
+    one-ulp self-sensitivity (floor 1e-6 in inputs that span [4,7] x [70,100])."""
     from gp_rto_ei_b200.sub_uts import systems as S
     g = load_golden('rto_wo.npz')
     np.random.seed(0); random.seed(0)
@@ -269,4 +289,4 @@ def test_rto_episode_williams_otto_configuration(u2, tag, acq, noisy):
     print('\n[rto %s] max |dX| vs reference: %.3e (reference one-ulp self-sensitivity %.3e)' % (tag, err, sens))
     assert np.allclose(np.array(TR_l, dtype=float), g[tag + '_TR_l'], rtol=0, atol=1e-15)
     assert list(backtrack) == list(g[tag + '_backtrack'])
-    assert err < max(100 * sens, 1e-5)
+    assert err < max(10 * sens, 1e-6)
