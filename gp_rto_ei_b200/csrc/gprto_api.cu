@@ -210,6 +210,7 @@ int nlml_device(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, co
   if (B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
     int rc = GPRTO_EUNSUPPORTED;
+    if (h->k3_path == 3) rc = launch_nlml_lb(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead + DMMA panel solve
     if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead kernel
     if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
@@ -296,7 +297,7 @@ int gprto_set_option(gprto_t* h, const char* name, int64_t value) {
   if (!h || !name) return GPRTO_EINVAL;
   if (!strcmp(name, "k4_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k4_path = int(value); return 0; }
   if (!strcmp(name, "cov_kernel")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->cov_kernel_kind = int(value); return 0; }
-  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
+  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 4) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
   if (!strcmp(name, "k2_path")) { if (value < 0 || value > 1) return GPRTO_EINVAL; h->k2_path = int(value); return 0; }
   return GPRTO_EINVAL;
 }

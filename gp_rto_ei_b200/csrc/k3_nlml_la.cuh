@@ -16,6 +16,9 @@
 #include "gprto_math.cuh"
 #include "k3_nlml_reg.cuh"
 #include <type_traits>
+#ifdef K3_TRACE
+#include <cstdlib>
+#endif
 
 #ifdef K3_TIMING
 #define K3LA_T0 long long tk[6] = {0, 0, 0, 0, 0, 0}; long long tprev = clock64();
@@ -26,6 +29,18 @@
 #endif
 
 namespace gprto {
+
+// -DK3_TRACE: absolute clock64 time stamps of one CTA (block K3_TRACE_BS), per warp / block step / event, for the
+// timeline analysis of tools/k3_trace.py (debug builds only; the accessor below is not part of the ABI)
+#ifdef K3_TRACE
+#ifndef K3_TRACE_BS
+#define K3_TRACE_BS 20000
+#endif
+__device__ long long g_k3_trace[8 * 32 * 8];
+#define K3TR(kb, ev) { if (bs == K3_TRACE_BS && lane == 0) g_k3_trace[((tid >> 5) * 32 + (kb)) * 8 + (ev)] = clock64(); }
+#else
+#define K3TR(kb, ev)
+#endif
 
 // warps per CTA: 1 panel + W-1 update warps.  8 for every size: at NT = 8..14 that is more warps (and fewer tiles, i.e.
 // registers, per warp) than the NT/2 of the plain register kernel, which buys a third resident CTA at NT = 8.
@@ -205,22 +220,30 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
     double pm = 1.0;
     int pe = 0, info = 0;
     K3LA_T0
+    K3TR(31, 0)
     k3la_bar_sync(1, ATHREADS);                                         // X(-1): column 0 is in panel buffer 0
+    K3TR(31, 1)
     k3_diag_tile_lean(P + 0, LDP, rinv_s, lane, 0, pm, pe, info);
     if (lane == 0 && info) s_info = info;
+    K3TR(31, 2)
     k3la_bar_sync(2, ATHREADS);                                         // Y(-1)
+    K3TR(31, 3)
 #pragma unroll 1
     for (int kb = 0; kb + 1 < NT; ++kb) {
       if (s_info != 0) break;
       double* nbuf = P + ((kb + 1) & 1) * NP * LDP;
       K3LA_MARK(0)
+      K3TR(kb, 0)
       k3la_bar_sync(1, ATHREADS);                                       // X(kb): column kb+1 updated and spilled
       K3LA_MARK(1)
+      K3TR(kb, 1)
       k3_diag_tile_lean(nbuf + 8 * (kb + 1) * LDP, LDP, rinv_s, lane, 8 * (kb + 1), pm, pe, info);
       if (lane == 0 && info) s_info = info;
       K3LA_MARK(2)
+      K3TR(kb, 2)
       k3la_bar_sync(2, ATHREADS);                                       // Y(kb)
       K3LA_MARK(3)
+      K3TR(kb, 3)
     }
     k3la_bar_sync(4, ATHREADS);                                         // F: the update warps have finished z (quad_s)
 #ifdef K3_TIMING
@@ -239,6 +262,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   const int uw = (IDLE_W >= 0 && w > IDLE_W) ? w - 1 : w, utid = 32 * uw + lane;
   const double c0 = 2.0 * theta[d];
   const double diag_add = exp_det(2.0 * theta[d + 1]) + jitter;
+  K3TR(31, 0)
   double C0[SLOTS], C1[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
@@ -271,6 +295,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
     C1[s] = in1 ? v1 : (i == j0 + 1 ? 1.0 : 0.0);
   }
   // prologue: spill column 0 (tiles tau < NT), let the panel warp factor it, solve the panel rows of column 0
+  K3TR(31, 1)
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int tau = s * UW + uw;
@@ -278,6 +303,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   }
   k3la_bar_arrive(1, ATHREADS);                                         // X(-1)
   k3la_bar_sync(2, ATHREADS);                                           // Y(-1): L11(0), rinv, z_0 ready
+  K3TR(31, 2)
   K3LA_T0
 
 #pragma unroll 1
@@ -286,6 +312,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
     double* buf = P + (kb & 1) * NP * LDP;
     double* nbuf = P + ((kb + 1) & 1) * NP * LDP;
     const double* zs = zs2 + (kb & 1) * 16;
+    K3TR(kb, 0)
     // (3) panel rows of column kb: L21 = A21 L11^-T, one thread per remaining row; the thread after the last row solves
     // the right-hand side block the same way (y is the extra row of the augmented matrix): z_kb = L11^-1 y'_kb
     {
@@ -324,8 +351,10 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
       }
     }
     K3LA_MARK(0)
+    K3TR(kb, 1)
     k3la_bar_sync(3, UTHREADS);                                        // Z(kb): panel kb complete (update warps only)
     K3LA_MARK(1)
+    K3TR(kb, 2)
     if (kb + 1 == NT) break;
     // (4) trailing update.  This warp's tiles are tau = s UW + uw in column-major order, so the active ones (tau >=
     // off1) are a contiguous range of slots starting at s_lo, the tiles of column kb+1 coming first: jump straight to
@@ -341,6 +370,7 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
       if (tau >= TILES) return false;
       if (!arrived && tau >= off2) {
         K3LA_MARK(2)
+        K3TR(kb, 3)
         k3la_bar_arrive(1, ATHREADS);                                   // X(kb): hand column kb+1 to the panel warp
         arrived = true;
       }
@@ -368,11 +398,14 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   k3la_done:
     if (!arrived) {
       K3LA_MARK(2)
+      K3TR(kb, 3)
       k3la_bar_arrive(1, ATHREADS);
     }
     K3LA_MARK(3)
+    K3TR(kb, 4)
     k3la_bar_sync(2, ATHREADS);                                         // Y(kb): diag(kb+1) done, all updates done
     K3LA_MARK(4)
+    K3TR(kb, 5)
   }
   k3la_bar_arrive(4, ATHREADS);                                       // F
 #ifdef K3_TIMING
@@ -383,8 +416,16 @@ k3_nlml_la_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
 template <int NT, int DT>
 int launch_k3la_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                   double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
-  const size_t smem = k3la_smem_bytes<NT>(d);
+  size_t smem = k3la_smem_bytes<NT>(d);
   static PerDeviceOnce once;
+#ifdef K3_TRACE
+  // occupancy experiment: GPRTO_K3_SMEM_PAD=<bytes> pads the dynamic shared memory (120000 -> one CTA per SM)
+  size_t pad = getenv("GPRTO_K3_SMEM_PAD") ? size_t(atol(getenv("GPRTO_K3_SMEM_PAD"))) : 0;
+  if (pad > smem) {
+    cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pad));
+    smem = pad;
+  }
+#endif
   if (once.first()) {
     if (k3la_smem_bytes<NT>(K3R_MAXD) > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k3_nlml_la_kernel<NT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
