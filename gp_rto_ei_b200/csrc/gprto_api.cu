@@ -210,8 +210,12 @@ int nlml_device(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, co
   if (B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
     int rc = GPRTO_EUNSUPPORTED;
-    if (h->k3_path == 3) rc = launch_nlml_lb(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead + DMMA panel solve
-    if (h->k3_path == 0) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);     // look-ahead kernel
+    // auto: look-ahead kernel with the tensor-core panel solve (k3_nlml_lb.cuh) where it measured faster than the plain
+    // register kernel (B200, d = 3: n = 33..64 and n > 80; at n = 65..80 the two are level and the plain one is kept);
+    // 3 forces it, 4 selects the round-1 look-ahead kernel (k3_nlml_la.cuh, kept as a cross-check), 2 the plain kernel
+    if (h->k3_path == 3 || (h->k3_path == 0 && (n <= 64 || n > 80)))
+      rc = launch_nlml_lb(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    if (h->k3_path == 4) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
   }
