@@ -210,11 +210,12 @@ int nlml_device(gprto_t* h, int64_t B, int S, int n, int d, const double* Xn, co
   if (B * int64_t(S) > kMaxGridX) return GPRTO_EUNSUPPORTED;
   if (h->k3_path != 1 && n <= K3R_MAXN && d <= K3R_MAXD) {
     int rc = GPRTO_EUNSUPPORTED;
-    // auto: look-ahead kernel with the tensor-core panel solve (k3_nlml_lb.cuh) where it measured faster than the plain
-    // register kernel (B200, d = 3: n = 33..64 and n > 80; at n = 65..80 the two are level and the plain one is kept);
-    // 3 forces it, 4 selects the round-1 look-ahead kernel (k3_nlml_la.cuh, kept as a cross-check), 2 the plain kernel
-    if (h->k3_path == 3 || (h->k3_path == 0 && (n <= 64 || n > 80)))
-      rc = launch_nlml_lb(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    // auto: n > 32 -> "lc" (k3_nlml_lc.cuh: pivot chain in one warp, tensor-core panel solve, three CTAs per SM), measured
+    // faster than every other path at every size (B200, d = 3, evals/s lc / round-1 kernels: n = 40 5.6e7 / 4.8e7,
+    // 64 4.0e7 / 3.3e7, 80 2.9e7 / 2.1e7, 96 2.1e7 / 1.4e7, 112 1.6e7 / 1.1e7, 128 1.23e7 / 0.84e7); n <= 32 -> plain register
+    // kernel.  Forced paths (cross-checks in the tests): 2 plain register kernel, 3 "lb", 4 round-1 look-ahead kernel, 5 "lc".
+    if (h->k3_path == 5 || h->k3_path == 0) rc = launch_nlml_lc(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
+    if (h->k3_path == 3) rc = launch_nlml_lb(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (h->k3_path == 4) rc = launch_nlml_la(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (rc == GPRTO_EUNSUPPORTED) rc = launch_nlml_reg(B, S, n, d, Xn, Yn, theta, jitter, nll, status, s, gidx);
     if (rc != GPRTO_EUNSUPPORTED) { h->launches++; return rc; }
@@ -301,7 +302,7 @@ int gprto_set_option(gprto_t* h, const char* name, int64_t value) {
   if (!h || !name) return GPRTO_EINVAL;
   if (!strcmp(name, "k4_path")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->k4_path = int(value); return 0; }
   if (!strcmp(name, "cov_kernel")) { if (value < 0 || value > 2) return GPRTO_EINVAL; h->cov_kernel_kind = int(value); return 0; }
-  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 4) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
+  if (!strcmp(name, "k3_path")) { if (value < 0 || value > 5) return GPRTO_EINVAL; h->k3_path = int(value); return 0; }
   if (!strcmp(name, "k2_path")) { if (value < 0 || value > 1) return GPRTO_EINVAL; h->k2_path = int(value); return 0; }
   return GPRTO_EINVAL;
 }

@@ -35,6 +35,8 @@ int launch_nlml_reg(int64_t B, int S, int n, int d, const double* Xn, const doub
                     int32_t* status, cudaStream_t s, const int32_t* gidx);
 int launch_nlml_lb(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter, double* nll,
                    int32_t* status, cudaStream_t s, const int32_t* gidx);
+int launch_nlml_lc(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter, double* nll,
+                   int32_t* status, cudaStream_t s, const int32_t* gidx);
 // K2 register-tile / DMMA factor kernel (32 < n <= 128; GPRTO_EUNSUPPORTED otherwise)
 int launch_factor_la(int64_t B, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter, double* invK,
                      double* alpha, double* logdet, int32_t* status, cudaStream_t s);

@@ -54,7 +54,7 @@ const char* gprto_error_string(int code);
  * [3] = max d. */
 int  gprto_limits(int64_t limits[4]);
 int  gprto_set_option(gprto_t* h, const char* name, int64_t value);   /* "k4_path": GPRTO_K4_*; "k3_path": 0 auto, 1 generic (shared memory), 2 register kernel without look-ahead,
-                                                                         3 look-ahead kernel with tensor-core panel solve (forced), 4 round-1 look-ahead kernel;
+                                                                         3 look-ahead kernel with tensor-core panel solve ("lb"), 4 round-1 look-ahead kernel, 5 "lc" (= auto for n > 32);
                                                                          "k2_path": 0 auto (register-tile / DMMA kernel for 32 < n <= 128), 1 generic (shared memory);
                                                                          "cov_kernel": kernel of gprto_cov_se_ard only: 0 SE-ARD, 1 Matern-3/2, 2 Matern-5/2 */
 /* Number of kernels this library launched through the handle since creation (bench.py's gpu_launches). */

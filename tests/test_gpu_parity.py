@@ -278,7 +278,7 @@ def _check_nlml(handle, dev, X, y, thetas, ref, fail, label):
     """X[B,n,d], y[B,n], thetas[B,S,d+2]; ref[B,S]."""
     nz = handle.normalise(T(X, dev), T(y, dev))
     worst = 0.0
-    for k3 in (0, 1, 2, 4):
+    for k3 in (0, 1, 2, 3, 4):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(thetas, dev))
         handle.set_option('k3_path', 0)
@@ -337,7 +337,7 @@ def test_k3_status_flags_non_positive_definite(handle, dev):
     y = np.array([[1.0, 2.0, 0.5, -1.0]])
     nz = handle.normalise(T(X, dev), T(y, dev))
     theta = np.array([[[0.0, 0.0, 0.0, -400.0], [0.0, 0.0, 0.0, -2.0]]])
-    for k3 in (0, 1, 2, 4):
+    for k3 in (0, 1, 2, 3, 4):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(theta, dev), jitter=0.0)
         handle.set_option('k3_path', 0)
@@ -630,7 +630,7 @@ def test_k3_lookahead_kernel_reports_failures_without_hanging(handle, dev, n, ba
     nz = handle.normalise(T(X, dev), T(y, dev))
     theta = np.tile(np.array([0.0, 0.0, 0.0, 0.0, -400.0]), (2, 1, 1))
     theta[1, 0, 4] = -2.0
-    for k3 in (0, 2, 4):
+    for k3 in (0, 2, 3, 4):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(theta, dev), jitter=-1e-3)
         handle.set_option('k3_path', 0)
@@ -671,7 +671,7 @@ def test_k3_lookahead_kernel_generic_dimension(handle, dev, n, d):
     th = np.concatenate([rng.uniform(-0.3, 0.8, (2, 3, d)), rng.uniform(-0.3, 0.3, (2, 3, 1)), rng.uniform(-3.4, -2.3, (2, 3, 1))], axis=2)
     nz = handle.normalise(T(X, dev), T(y, dev))
     res = []
-    for k3 in (0, 1, 2, 4):
+    for k3 in (0, 1, 2, 3, 4):
         handle.set_option('k3_path', k3)
         nll, st = handle.nlml(nz['Xn'], nz['Yn'], T(th, dev))
         handle.set_option('k3_path', 0)

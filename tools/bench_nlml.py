@@ -50,7 +50,7 @@ def main():
     F = a.n ** 3 / 3 + 2 * a.n ** 2 + (a.n ** 2 / 2) * (3 * a.d + 2) + 4 * a.n
     evals = a.B * a.S
     print(json.dumps({'metric': 'NLML evals/s (FP64, batched)', 'value': evals / (ms * 1e-3), 'ms_per_sweep': ms, 'B': a.B, 'S': a.S, 'n': a.n,
-                      'd': a.d, 'path': {0: 'auto', 1: 'generic', 2: 'reg', 3: 'lb (look-ahead + DMMA panel solve)', 4: 'reserved'}[a.path], 'flops_per_eval': F, 'achieved_tflops': evals * F / (ms * 1e-3) / 1e12,
+                      'd': a.d, 'path': {0: 'auto', 1: 'generic', 2: 'reg', 3: 'lb (look-ahead + DMMA panel solve)', 4: 'la (round-1 look-ahead)', 5: 'lc (pivot chain in one warp)'}[a.path], 'flops_per_eval': F, 'achieved_tflops': evals * F / (ms * 1e-3) / 1e12,
                       'failed': int((st != 0).sum()), 'nan': int(torch.isnan(nll).sum()), 'argmin_hist_first8': bi[:8].tolist(), 'check': check}))
 
 
