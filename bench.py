@@ -55,6 +55,15 @@ def flops_nlml(n, d):
     return n ** 3 / 3 + 2 * n * n + (n * n / 2) * (3 * d + 2) + 4 * n
 
 
+def k3_kernel_name(n, d):
+    """Instance the dispatcher launches for n > 32 (gprto_api.cu: nlml_device -> k3_nlml_lc.cuh)."""
+    nt = (n + 15) // 16 * 2
+    tiles = nt * (nt + 1) // 2
+    slots = (tiles - nt + 6) // 7
+    rs = 7 if nt >= 12 else (4 if nt == 10 else slots)
+    return 'k3_nlml_lc_kernel<%d,%d,%d>' % (nt, d if d in (2, 3) else 0, rs) if n > 32 else 'k3_nlml_tile_kernel<%d,%d>' % (nt, d if d in (2, 3) else 0)
+
+
 def fp64_peak():
     """FP64 roofline denominator: MEASURED_PEAKS.json carries HBM and bf16 only, so the FP64 figure is the one
     measured on this pool's B200 by tools/fp64_peaks.cu (DMMA.8x8x4 and DFMA share one pipe: 37.1 / 36.7 TFLOP/s)."""
@@ -371,11 +380,11 @@ def nlml_block(c, B, S, n, d, steps, warmup, label, with_e2e=True):
     failed = sum_over_ranks(c, float((st['status'] != 0).sum()))
     out = {'metric': METRIC_CFG4, 'workload': label, 'value': evals / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'n_gpus': c.world,
            'gps_per_gpu': B, 'starts': S, 'n': n, 'd': d, 'flops_per_eval': F, 'gpu_launches': launches,
-           'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'kernel': 'k3_nlml_la_kernel<%d,%d>' % ((n + 15) // 16 * 2, d),
+           'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'kernel': k3_kernel_name(n, d),
                         'kernel_ms': k_ms, 'peak_source': 'FP64 ' + peak_src},
            'failed_factorisations': int(failed),
            'note_failures': 'corners of the reference hyper-parameter box (sn2 = e^-16, sf2 = e^10) are indefinite in FP64; the reference would raise there (utilities_2.py:107)'}
-    tr, src = ncu_traffic('k3_ncu_summary.json', 'k3_nlml_la_kernel', float(B) * S)
+    tr, src = ncu_traffic('k3_ncu_summary.json', 'k3_nlml_lc_kernel', float(B) * S)
     out['roofline']['traffic'] = tr
     out['roofline']['traffic_source'] = src
     if with_e2e:
