@@ -26,17 +26,101 @@
 
 namespace gprto {
 
-// RS = number of tile slots per warp kept in registers (the slots of the LAST tile columns, which live longest and are
-// updated most often); the remaining slots - the early columns, few updates each - live in shared memory.  RS < SLOTS trades
-// some shared-memory traffic for registers: n = 128 fits three CTAs per SM instead of two with RS = 7.
+// Dealing of the tiles to the 7 update warps.  Shipped: one by one in reversed column-major order (columns from the last to
+// the first, rows from the bottom up, the diagonal tile last within its column), so that the tiles alive at step kb
+// (J >= kb+2) are a prefix of every warp's slots and the tiles of column kb+1 follow.  Measured alternative (BY_ROWS): whole
+// tile ROWS per warp, longest row first to the least loaded warp - consecutive slots then share the A fragment L(I, kb),
+// which is reloaded only when the row changes (the trailing loop is bound by shared-memory bandwidth,
+// profiles/r02_k3_timeline.md par. 4).  It cut the operand loads by ~45 % but costs balance (21 / 19 tiles per warp instead
+// of 20 / 19 at n = 128, and late rows stay long while early ones die): n = 128 1.19e7 evals/s against 1.24e7, n = 96
+// 2.15e7 against 2.12e7 - not shipped.
 template <int NT>
-constexpr int k3lc_rs() { return NT >= 12 ? 7 : (NT == 10 ? 4 : K3LB<NT>::SLOTS); }
+struct K3Deal {
+  static constexpr int UW = 7;
+  static constexpr bool BY_ROWS = false;                // see above
+  int owner[NT];
+  int count[UW];
+  int rows[UW];
+  int slots_all, slots;
+  constexpr K3Deal() : owner{}, count{}, rows{}, slots_all(0), slots(0) {
+    for (int I = NT - 1; I >= 0; --I) {
+      int u = 0;
+      for (int v = 1; v < UW; ++v)
+        if (count[v] < count[u]) u = v;
+      owner[I] = u;
+      count[u] += I + 1;
+      rows[u] += 1;
+    }
+    for (int u = 0; u < UW; ++u) {
+      if (count[u] > slots_all) slots_all = count[u];
+      if (count[u] - rows[u] > slots) slots = count[u] - rows[u];
+    }
+    if (!BY_ROWS) {                                     // tiles dealt one by one in reversed column-major order
+      slots_all = (NT * (NT + 1) / 2 + UW - 1) / UW;
+      slots = (NT * (NT + 1) / 2 - NT + UW - 1) / UW;
+    }
+  }
+};
+
+template <int NT>
+struct K3LC {
+  static constexpr K3Deal<NT> deal{};
+  static constexpr int UW = 7;
+  static constexpr int SLOTS_ALL = deal.slots_all;        // most tiles any warp owns
+  static constexpr int SLOTS = deal.slots;                // most tiles outside tile column 0 (those never enter registers)
+  static constexpr int TABN = (SLOTS_ALL + 2) * UW;       // tile table, padded (the prefetch runs two slots ahead)
+  static constexpr int STABN = NT * UW;
+  // RS = number of slots per warp kept in registers (the last tile columns: they live longest and are updated most often);
+  // the remaining slots - early columns, few updates each - live in shared memory: n = 128 fits three CTAs per SM.
+  static constexpr int RS = NT >= 12 ? 7 : (NT == 10 ? 4 : SLOTS);
+};
+
+constexpr uint32_t K3LC_VALID = 1u << 15, K3LC_ARRIVE = 1u << 14, K3LC_OFFMASK = 0x3fff;
+
+// Host: tile table [TABN] (byte offset 768 I | flags, 768 J << 16; entry s * UW + u = slot s of warp u) followed by the
+// step table [NT][UW] (nact | nspill << 5 | diag2 << 10).
+template <int NT>
+void k3lc_build_tables(uint32_t* tab) {
+  constexpr K3Deal<NT> deal{};
+  constexpr int UW = 7, TABN = K3LC<NT>::TABN;
+  for (int e = 0; e < TABN + NT * UW; ++e) tab[e] = 0;
+  int cntJ2[UW] = {};
+  int lists[UW][K3LC<NT>::SLOTS_ALL + 1][2];
+  int len[UW] = {};
+  int k = 0;                                            // position in the global order: columns from the last to the first,
+  for (int J = NT - 1; J >= 0; --J)                     // rows from the bottom up, the diagonal tile last within its column
+    for (int I = NT - 1; I >= J; --I, ++k) {
+      const int u = K3Deal<NT>::BY_ROWS ? deal.owner[I] : k % UW;
+      lists[u][len[u]][0] = I; lists[u][len[u]][1] = J; ++len[u];
+    }
+  for (int u = 0; u < UW; ++u) {
+    for (int s = 0; s < len[u]; ++s) {
+      tab[s * UW + u] = uint32_t(64 * K3R_LDP * lists[u][s][0]) | K3LC_VALID | (uint32_t(64 * K3R_LDP * lists[u][s][1]) << 16);
+      if (lists[u][s][1] >= 2) ++cntJ2[u];
+    }
+    tab[cntJ2[u] * UW + u] |= K3LC_ARRIVE;              // first slot (from the top) with J <= 1: X'(-1) after it
+  }
+  for (int kb = 0; kb < NT; ++kb)
+    for (int u = 0; u < UW; ++u) {
+      int nall = 0, n4b = 0;
+      for (int s = 0; s < len[u]; ++s) {
+        if (lists[u][s][1] >= kb + 1) ++nall;
+        if (lists[u][s][1] >= kb + 2) ++n4b;
+      }
+      bool diag_owner = false, d2 = false;
+      for (int s = 0; s < len[u]; ++s) {
+        if (lists[u][s][0] == kb + 1 && lists[u][s][1] == kb + 1) diag_owner = true;
+        if (lists[u][s][0] == kb + 2 && lists[u][s][1] == kb + 2) d2 = true;
+      }
+      tab[TABN + kb * UW + u] = uint32_t(nall - (diag_owner ? 1 : 0)) | (uint32_t(n4b - (d2 ? 1 : 0)) << 5) | (d2 ? 1u << 10 : 0u);
+    }
+}
 
 template <int NT, int RS>
 constexpr size_t k3lc_smem_bytes(int d) {
   return sizeof(double) * (2 * size_t(8 * NT) * K3R_LDP + 4 * 8 * K3R_LDP + size_t(8 * NT) * d + 2 * 8 * NT + 16 + 16 + 2 +
-                           size_t(K3LB<NT>::SLOTS - RS) * K3LB<NT>::UW * 64) +
-         4 * K3LB<NT>::TABN + 4 * NT * K3LB<NT>::UW + 16;
+                           size_t(K3LC<NT>::SLOTS - RS) * 7 * 64) +
+         4 * K3LC<NT>::TABN + 4 * NT * 7 + 16;
 }
 
 // exp for the kernel matrix: exp_det without the overflow clamp (the argument is 2 log sf - r^2/2 <= 2 log sf < 709 inside the
@@ -115,15 +199,14 @@ __device__ __forceinline__ void k3_diag_tile_inv_regs(double x0, double x1, doub
 }
 
 template <int NT, int DT, int RS>
-__global__ void __launch_bounds__(K3LB<NT>::THREADS, ((NT <= 8 || RS < K3LB<NT>::SLOTS) ? 3 : 2))
+__global__ void __launch_bounds__(K3LB<NT>::THREADS, ((NT <= 8 || RS < K3LC<NT>::SLOTS) ? 3 : 2))
 k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const double* __restrict__ Yn,
                   const double* __restrict__ theta_all, double jitter, double* __restrict__ nll,
-                  int32_t* __restrict__ status, const int32_t* __restrict__ gidx) {
-  using C = K3LB<NT>;
-  constexpr int UW = C::UW, TILES = C::TILES, SLOTS = C::SLOTS, SLOTS_ALL = C::SLOTS_ALL, NP = C::NP, LDP = K3R_LDP;
-  constexpr int THREADS = C::THREADS, TABN = C::TABN;
-  constexpr int UTHREADS = 32 * UW, ATHREADS = 32 * (UW + 1), PANEL_W = C::W - 1;
-  constexpr int S1 = (TILES - 1 - NT) / UW;                             // slot of tile (1,1); column 0 lives in slots >= S1
+                  int32_t* __restrict__ status, const int32_t* __restrict__ gidx, const uint32_t* __restrict__ tables) {
+  using C = K3LC<NT>;
+  constexpr int UW = C::UW, SLOTS = C::SLOTS, SLOTS_ALL = C::SLOTS_ALL, NP = 8 * NT, LDP = K3R_LDP;
+  constexpr int THREADS = K3LB<NT>::THREADS, TABN = C::TABN;
+  constexpr int UTHREADS = 32 * UW, ATHREADS = 32 * (UW + 1), PANEL_W = K3LB<NT>::W - 1;
   const int d = DT > 0 ? DT : d_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* P = reinterpret_cast<double*>(smem_raw);   // [2][NP][LDP]
@@ -136,7 +219,7 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   double* nhw = zall + NP;                           // [16]
   double* quad_s = nhw + 16;                         // [2]: |z|^2
   double* spare = quad_s + 2;                        // [16]
-  uint32_t* tOff = reinterpret_cast<uint32_t*>(spare + 16);   // [TABN]: byte offsets (768 I) | (768 J) << 16 of reversed tile tau_r
+  uint32_t* tOff = reinterpret_cast<uint32_t*>(spare + 16);   // [TABN]: slot s of warp u at s * UW + u: byte offset 768 I | flags, 768 J << 16
   uint32_t* stab = tOff + TABN;                      // [NT][UW]: per (step, warp) constants
   __shared__ int s_inf[2];                           // dpotrf code of the diagonal tile of column kb, slot kb & 1
 
@@ -150,31 +233,7 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   for (int e = tid; e < NP; e += THREADS) ys[e] = e < n ? Yn[b * n + e] : 0.0;
   if (tid < d) nhw[tid] = -0.5 * exp_det(-2.0 * theta[tid]);
   if (tid == 0) { s_inf[0] = 0; s_inf[1] = 0; quad_s[0] = 0.0; }
-  for (int e = tid; e < TABN; e += THREADS) {        // reversed column-major order: tau = TILES-1-e = off(J) + (I - J)
-    int J = 0, I = 0;
-    if (e < TILES) {
-      const int tau = TILES - 1 - e;
-      while ((J + 1) * NT - (J + 1) * J / 2 <= tau) ++J;
-      I = J + tau - (J * NT - J * (J - 1) / 2);
-    }
-    tOff[e] = uint32_t(64 * LDP * I) | (uint32_t(64 * LDP * J) << 16);      // byte offsets of tile rows 8 I, 8 J in a panel
-  }
-  for (int e = tid; e < NT * UW; e += THREADS) {
-    // step kb, update warp u: live slots of the warp in reversed order = [trailing tiles right of column kb+2 | diag2 tile
-    // (kb+2, kb+2), last trailing slot of its owner | tiles of column kb+1]; the diagonal tile (kb+1, kb+1) - the warp's very
-    // last live slot - belongs to the panel warp and is left out.  nact slots are updated, those from nspill on are spilled
-    // (the first of them to the side buffer if the warp owns the diag2 tile).
-    const int kb = e / UW, u = e % UW;
-    const int off1 = (kb + 1) * NT - (kb + 1) * kb / 2, off2 = (kb + 2) * NT - (kb + 2) * (kb + 1) / 2;
-    const int last4b = TILES - 1 - off2, lastcol = TILES - 1 - off1;       // largest tau_r of each group (-1: none)
-    const int n4b = last4b >= u ? (last4b - u) / UW + 1 : 0;
-    const int nall = lastcol >= u ? (lastcol - u) / UW + 1 : 0;
-    const bool diag_owner = lastcol >= 0 && lastcol % UW == u;
-    const bool d2 = last4b >= 0 && last4b % UW == u;
-    const int nact = nall - (diag_owner ? 1 : 0);
-    const int nspill = n4b - (d2 ? 1 : 0);
-    stab[e] = uint32_t(nact) | (uint32_t(nspill) << 5) | (d2 ? 1u << 10 : 0u);
-  }
+  for (int e = tid; e < TABN + NT * UW; e += THREADS) tOff[e] = tables[e];      // tile table + step table (contiguous)
   __syncthreads();
 
   const int fsrc = 4 * g + (t >> 1);                                    // accumulator -> fragment shuffle source
@@ -246,48 +305,48 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
     // slots from high to low: tile column 0 and tile (1,1) come first and are handed to the panel warp at once
 #pragma unroll
     for (int s = SLOTS_ALL - 1; s >= 0; --s) {
-      const int taur = s * UW + uw;
-      const uint32_t ij = tOff[taur];
-      const int I8 = int(((ij & 0xffff) * 683u) >> 16), J8 = int(((ij >> 16) * 683u) >> 16);      // 8 I, 8 J  (768 I * 683 >> 16)
-      const int i = I8 + g, j0 = J8 + 2 * t;
-      const double* xi = Xs + i * d;
-      const double* xj = Xs + j0 * d;
-      double a0 = c0, a1 = c0;
-      if (DT > 0) {
+      const uint32_t ij = tOff[s * UW + uw];
+      const uint32_t oI = ij & K3LC_OFFMASK, oJ = ij >> 16;
+      const int I8 = int((oI * 683u) >> 16), J8 = int((oJ * 683u) >> 16);      // 8 I, 8 J  (768 I * 683 >> 16)
+      {                                                                 // (a padding entry evaluates tile (0,0) again; nothing of it is stored)
+        const int i = I8 + g, j0 = J8 + 2 * t;
+        const double* xi = Xs + i * d;
+        const double* xj = Xs + j0 * d;
+        double a0 = c0, a1 = c0;
+        if (DT > 0) {
 #pragma unroll
-        for (int dd = 0; dd < (DT > 0 ? DT : 1); ++dd) {
-          const double x = xi[dd], h = hw[dd];
-          const double d0 = x - xj[dd], d1 = x - xj[DT + dd];
-          a0 = fma(d0 * d0, h, a0);
-          a1 = fma(d1 * d1, h, a1);
+          for (int dd = 0; dd < (DT > 0 ? DT : 1); ++dd) {
+            const double x = xi[dd], h = hw[dd];
+            const double d0 = x - xj[dd], d1 = x - xj[DT + dd];
+            a0 = fma(d0 * d0, h, a0);
+            a1 = fma(d1 * d1, h, a1);
+          }
+        } else {
+          for (int dd = 0; dd < d; ++dd) {
+            const double x = xi[dd], h = nhw[dd];
+            const double d0 = x - xj[dd], d1 = x - xj[d + dd];
+            a0 = fma(d0 * d0, h, a0);
+            a1 = fma(d1 * d1, h, a1);
+          }
         }
-      } else {
-        for (int dd = 0; dd < d; ++dd) {
-          const double x = xi[dd], h = nhw[dd];
-          const double d0 = x - xj[dd], d1 = x - xj[d + dd];
-          a0 = fma(d0 * d0, h, a0);
-          a1 = fma(d1 * d1, h, a1);
+        double k0 = k3lc_exp(a0), k1 = k3lc_exp(a1);
+        if (I8 == J8 || I8 + 8 > n) {                                   // (warp-uniform) diagonal tile or padded rows / columns
+          k0 += (i == j0 ? diag_add : 0.0);
+          k1 += (i == j0 + 1 ? diag_add : 0.0);
+          const bool in0 = i < n && j0 < n, in1 = i < n && j0 + 1 < n;
+          k0 = in0 ? k0 : (i == j0 ? 1.0 : 0.0);
+          k1 = in1 ? k1 : (i == j0 + 1 ? 1.0 : 0.0);
         }
+        if (s < RS) { C0[s] = k0; C1[s] = k1; }
+        else if (s < SLOTS) *reinterpret_cast<double2*>(csm + (s - RS) * UW * 64) = make_double2(k0, k1);
+        if ((K3Deal<NT>::BY_ROWS || s >= SLOTS - 1) && oJ == 0 && (ij & K3LC_VALID))      // tile column 0 goes straight to panel buffer 0
+          *reinterpret_cast<double2*>(&P[(I8 + g) * LDP + 2 * t]) = make_double2(k0, k1);
+        if ((K3Deal<NT>::BY_ROWS || s == (NT * (NT + 1) / 2 - 1 - NT) / UW) && oI == 64 * LDP && oJ == 64 * LDP)      // tile (1,1): no update before the panel warp takes it
+          *reinterpret_cast<double2*>(&Dq[8 * LDP + g * LDP + 2 * t]) = make_double2(k0, k1);
       }
-      double k0 = k3lc_exp(a0), k1 = k3lc_exp(a1);
-      if (I8 == J8 || I8 + 8 > n) {                                     // (warp-uniform) diagonal tile or padded rows / columns
-        k0 += (i == j0 ? diag_add : 0.0);
-        k1 += (i == j0 + 1 ? diag_add : 0.0);
-        const bool in0 = i < n && j0 < n, in1 = i < n && j0 + 1 < n;
-        k0 = in0 ? k0 : (i == j0 ? 1.0 : 0.0);
-        k1 = in1 ? k1 : (i == j0 + 1 ? 1.0 : 0.0);
-      }
-      if (s < RS) { C0[s] = k0; C1[s] = k1; }
-      else if (s < SLOTS) *reinterpret_cast<double2*>(csm + (s - RS) * UW * 64) = make_double2(k0, k1);
-      // tile column 0 (tau_r >= TILES - NT) goes straight to panel buffer 0; only the slots from SLOTS-1 on can hold such tiles
-      if (s >= SLOTS - 1 && taur >= TILES - NT && taur < TILES)
-        *reinterpret_cast<double2*>(&P[(I8 + g) * LDP + 2 * t]) = make_double2(k0, k1);
-      // tile (1,1) = tau NT = tau_r TILES-1-NT: no update before the panel warp takes it
-      if (s == S1 && taur == TILES - 1 - NT)
-        *reinterpret_cast<double2*>(&Dq[8 * LDP + g * LDP + 2 * t]) = make_double2(k0, k1);
-      if (s == S1) {
+      if (ij & K3LC_ARRIVE) {
         K3TR(31, 3)
-        k3lb_bar_arrive(5, ATHREADS);                                   // X'(-1): column 0 and tile (1,1) are out
+        k3lb_bar_arrive(5, ATHREADS);                                   // X'(-1): this warp's tiles of columns 0 and 1 are out
       }
     }
   }
@@ -354,18 +413,20 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
       const uint32_t sp32 = (uint32_t)__cvta_generic_to_shared(nbuf + g * LDP + 2 * t);      // accumulator position in tile row 0
       const uint32_t dq32 = (uint32_t)__cvta_generic_to_shared(Dq + (kb & 1) * 8 * LDP + g * LDP + 2 * t);
       uint32_t ij = k3lb_lds32(tb32);
-      uint32_t offI = ij & 0xffff;
+      uint32_t offI = ij & K3LC_OFFMASK;
       uint32_t pa = fb32 + offI, pb = fb32 + (ij >> 16);
       double a0 = k3lb_lds64(pa), b0 = k3lb_lds64(pb), a1 = k3lb_lds64_32(pa), b1 = k3lb_lds64_32(pb);
       ij = k3lb_lds32(tb32 + 4 * UW);
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
         if (s >= nact) break;
-        const uint32_t offIn = ij & 0xffff;
+        const uint32_t offIn = ij & K3LC_OFFMASK;
         pa = fb32 + offIn;
         pb = fb32 + (ij >> 16);
         ij = k3lb_lds32(tb32 + 4 * (s + 2) * UW);
-        const double na0 = k3lb_lds64(pa), nb0 = k3lb_lds64(pb), na1 = k3lb_lds64_32(pa), nb1 = k3lb_lds64_32(pb);
+        double na0 = a0, na1 = a1;
+        if (!K3Deal<NT>::BY_ROWS || offIn != offI) { na0 = k3lb_lds64(pa); na1 = k3lb_lds64_32(pa); }      // same tile row: same A fragment
+        const double nb0 = k3lb_lds64(pb), nb1 = k3lb_lds64_32(pb);
         if (s < RS) {
           dmma884(C0[s < RS ? s : 0], C1[s < RS ? s : 0], a0, -b0);
           dmma884(C0[s < RS ? s : 0], C1[s < RS ? s : 0], a1, -b1);
@@ -405,10 +466,31 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   k3lb_bar_arrive(4, ATHREADS);                                         // F
 }
 
-template <int NT, int DT, int RS = k3lc_rs<NT>()>
+// Device copy of the tables of one NT (built on first use, one per device; a few hundred bytes, never freed)
+template <int NT>
+const uint32_t* k3lc_tables_device() {
+  static uint32_t* dev_tab[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!dev_tab[dev]) {
+    constexpr int N = K3LC<NT>::TABN + K3LC<NT>::STABN;
+    uint32_t host[N];
+    k3lc_build_tables<NT>(host);
+    uint32_t* p = nullptr;
+    if (cudaMalloc(&p, sizeof(host)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(p, host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(p); return nullptr; }
+    dev_tab[dev] = p;
+  }
+  return dev_tab[dev];
+}
+
+template <int NT, int DT, int RS = K3LC<NT>::RS>
 int launch_k3lc_d(int64_t B, int S, int n, int d, const double* Xn, const double* Yn, const double* theta, double jitter,
                   double* nll, int32_t* status, cudaStream_t s, const int32_t* gidx = nullptr) {
   const size_t smem = k3lc_smem_bytes<NT, RS>(d);
+  const uint32_t* tables = k3lc_tables_device<NT>();
+  if (!tables) return -static_cast<int>(cudaErrorMemoryAllocation);
   static PerDeviceOnce once;
   if (once.first()) {
     if (k3lc_smem_bytes<NT, RS>(K3R_MAXD) > 48 * 1024) {
@@ -418,7 +500,7 @@ int launch_k3lc_d(int64_t B, int S, int n, int d, const double* Xn, const double
     }
     cudaFuncSetAttribute(k3_nlml_lc_kernel<NT, DT, RS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  k3_nlml_lc_kernel<NT, DT, RS><<<(unsigned)(B * S), K3LB<NT>::THREADS, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx);
+  k3_nlml_lc_kernel<NT, DT, RS><<<(unsigned)(B * S), K3LB<NT>::THREADS, smem, s>>>(S, n, d, Xn, Yn, theta, jitter, nll, status, gidx, tables);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
