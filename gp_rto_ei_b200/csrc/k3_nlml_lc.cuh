@@ -24,6 +24,12 @@
 #pragma once
 #include "k3_nlml_lb.cuh"
 
+// Table-based exp in the evaluation of K: n = 128 1.265e7 evals/s against 1.246e7 with the polynomial-only exp_det, n = 64 level
+// (B200, d = 3); accuracy in the same class (0.98 ulp against < 1 ulp).  -DK3LC_TABLE_EXP=0 restores the bits of exp_det.
+#ifndef K3LC_TABLE_EXP
+#define K3LC_TABLE_EXP 1
+#endif
+
 namespace gprto {
 
 // Dealing of the tiles to the 7 update warps.  Shipped: one by one in reversed column-major order (columns from the last to
@@ -118,13 +124,45 @@ void k3lc_build_tables(uint32_t* tab) {
 
 template <int NT, int RS>
 constexpr size_t k3lc_smem_bytes(int d) {
-  return sizeof(double) * (2 * size_t(8 * NT) * K3R_LDP + 4 * 8 * K3R_LDP + size_t(8 * NT) * d + 2 * 8 * NT + 16 + 16 + 2 +
+  return sizeof(double) * (2 * size_t(8 * NT) * K3R_LDP + 4 * 8 * K3R_LDP + size_t(8 * NT) * d + 2 * 8 * NT + 16 + 32 + 2 +
                            size_t(K3LC<NT>::SLOTS - RS) * 7 * 64) +
          4 * K3LC<NT>::TABN + 4 * NT * 7 + 16;
 }
 
-// exp for the kernel matrix: exp_det without the overflow clamp (the argument is 2 log sf - r^2/2 <= 2 log sf < 709 inside the
-// reference's hyper-parameter box; same bits as exp_det there)
+// exp for the kernel matrix (K3LC_TABLE_EXP): a = (32 n + j) ln2/32 + r, |r| <= ln2/64, exp(a) = 2^n T[j] e^r
+// with T[j] = 2^(j/32) correctly rounded (32 doubles in shared memory) and e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120 +
+// r^4/720) (truncation 3e-18), result T + T (e^r - 1) in one fma: 0.98 ulp maximum error against mpmath over [-700, 10]
+// (exp_det: < 1 ulp), 11 FP64 operations instead of 15.  The argument is 2 log sf - r^2/2 <= 2 log sf < 709 inside the
+// reference's hyper-parameter box, so only the underflow side is clamped.
+__device__ const double k3lc_exp2_tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0,
+    0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0,
+    0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
+    0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+__device__ __forceinline__ double k3lc_exp_tab(double a, const double* tab) {
+  const double LOG2E32 = 0x1.71547652b82fep+5, LN2_32_HI = 0x1.62e42fc000000p-6, LN2_32_LO = 0x1.7d1cf79abc9e4p-33;
+  const double MAGIC = 6755399441055744.0;
+  const double tt = fma(a, LOG2E32, MAGIC);
+  const int m = __double2loint(tt);
+  const double mf = tt - MAGIC;
+  double r = fma(mf, -LN2_32_HI, a);
+  r = fma(mf, -LN2_32_LO, r);
+  const double T = tab[m & 31];
+  double sp = 1.0 / 720.0;
+  sp = fma(sp, r, 1.0 / 120.0);
+  sp = fma(sp, r, 1.0 / 24.0);
+  sp = fma(sp, r, 1.0 / 6.0);
+  sp = fma(sp, r, 0.5);
+  const double q = fma(r * r, sp, r);
+  const double res = fma(T, q, T);
+  const double sc = __hiloint2double(__double2hiint(res) + ((m >> 5) << 20), __double2loint(res));
+  return a < -700.0 ? 0.0 : sc;
+}
+
+// exp_det without the overflow clamp (same bits as exp_det for a < 709)
 __device__ __forceinline__ double k3lc_exp(double a) {
   const double LOG2E = 1.4426950408889634074, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
   const double MAGIC = 6755399441055744.0;
@@ -218,8 +256,8 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   double* zall = ys + NP;                            // [NP]: z = L^-1 y
   double* nhw = zall + NP;                           // [16]
   double* quad_s = nhw + 16;                         // [2]: |z|^2
-  double* spare = quad_s + 2;                        // [16]
-  uint32_t* tOff = reinterpret_cast<uint32_t*>(spare + 16);   // [TABN]: slot s of warp u at s * UW + u: byte offset 768 I | flags, 768 J << 16
+  double* etab = quad_s + 2;                         // [32]: 2^(j/32) (K3LC_TABLE_EXP)
+  uint32_t* tOff = reinterpret_cast<uint32_t*>(etab + 32);   // [TABN]: slot s of warp u at s * UW + u: byte offset 768 I | flags, 768 J << 16
   uint32_t* stab = tOff + TABN;                      // [NT][UW]: per (step, warp) constants
   __shared__ int s_inf[2];                           // dpotrf code of the diagonal tile of column kb, slot kb & 1
 
@@ -233,6 +271,9 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
   for (int e = tid; e < NP; e += THREADS) ys[e] = e < n ? Yn[b * n + e] : 0.0;
   if (tid < d) nhw[tid] = -0.5 * exp_det(-2.0 * theta[tid]);
   if (tid == 0) { s_inf[0] = 0; s_inf[1] = 0; quad_s[0] = 0.0; }
+#if K3LC_TABLE_EXP
+  if (tid < 32) etab[tid] = k3lc_exp2_tab[tid];
+#endif
   for (int e = tid; e < TABN + NT * UW; e += THREADS) tOff[e] = tables[e];      // tile table + step table (contiguous)
   __syncthreads();
 
@@ -329,7 +370,11 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
             a1 = fma(d1 * d1, h, a1);
           }
         }
+#if K3LC_TABLE_EXP
+        double k0 = k3lc_exp_tab(a0, etab), k1 = k3lc_exp_tab(a1, etab);
+#else
         double k0 = k3lc_exp(a0), k1 = k3lc_exp(a1);
+#endif
         if (I8 == J8 || I8 + 8 > n) {                                   // (warp-uniform) diagonal tile or padded rows / columns
           k0 += (i == j0 ? diag_add : 0.0);
           k1 += (i == j0 + 1 ? diag_add : 0.0);
