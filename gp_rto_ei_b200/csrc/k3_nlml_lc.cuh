@@ -22,6 +22,8 @@
 //     Z(kb)   panel kb solved in place (update warps wait; the panel warp arrives once it has stored tile (kb+1, kb))
 //     Y(kb)   the panel warp arrives when Linv(kb+1) is in Li[(kb+1)&1]; the update warps wait for it at the top of step kb+1
 #pragma once
+#include <mutex>
+
 #include "k3_nlml_lb.cuh"
 
 // Table-based exp in the evaluation of K: n = 128 1.265e7 evals/s against 1.246e7 with the polynomial-only exp_det, n = 64 level
@@ -515,6 +517,8 @@ k3_nlml_lc_kernel(int S, int n, int d_rt, const double* __restrict__ Xn, const d
 template <int NT>
 const uint32_t* k3lc_tables_device() {
   static uint32_t* dev_tab[64] = {};
+  static std::mutex mtx;                                // handles of several host threads may reach their first launch together
+  std::lock_guard<std::mutex> lock(mtx);
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
