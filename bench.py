@@ -661,7 +661,7 @@ def run_cfg3(args, c):
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                      'traffic_source': traffic_src, 'kernel': 'k4_dmma_kernel<8,3>', 'kernel_ms': k4_ms, 'flops_per_eval': F,
                      'executed_note': 'algorithmic flops (the reference\'s dense quadratic form); the kernel folds invK into a triangular matrix and executes '
-                                      '72 of 128 DMMA fragments per tile, so the executed pipe utilisation is the ncu figure (DMMA 47.7 % + FP64 38.6 % = 86 %)',
+                                      '72 of 128 DMMA fragments per tile, so the executed pipe utilisation is the ncu figure (DMMA 46.3 % + FP64 39.1 % = 85 %, profiles/k4_ncu_summary.json)',
                      'peak_source': 'FP64 ' + peak_src + '; FP64 DMMA and DFMA share one pipe on B200, MEASURED_PEAKS.json has no FP64 entry',
                      'hbm_check': {'algorithmic_bytes_per_eval': alg_bytes, 'achieved_gbs': float(B) * m * alg_bytes / (k4_ms * 1e-3) / 1e9,
                                    'peak_gbs': hbm, 'peak_source': hbm_src}},
